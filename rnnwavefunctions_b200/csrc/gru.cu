@@ -1,0 +1,364 @@
+// gru.cu — host launchers + utility kernels for the GRU wave functions (1-D pRNN, parity-symmetric pRNN,
+// 1-D RNN over a flattened 2-D lattice, complex cRNN) and the TFIM / J1-J2 local energies built on them.
+#include "gru_kernels.cuh"
+#include "host_util.cuh"
+#include "api_internal.h"
+
+namespace rnnwf {
+
+// ---------------------------------------------------------------------------------------------
+// utility kernels
+// ---------------------------------------------------------------------------------------------
+// samples [ns][N] -> sigT [ndir*tiles_s][N][M]; direction 1 holds the site-reversed configurations
+// (samples[:, ::-1], 1DTFIM/RNNwavefunction_paritysym.py:125).  Rows beyond ns are zero.
+__global__ void sig_transpose_kernel(const uint8_t* __restrict__ samples, uint8_t* __restrict__ sigT, int64_t ns, int N,
+                                     int M, int tiles_s, int ndir) {
+    const int64_t total = (int64_t)ndir * tiles_s * N * M;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i % M);
+        const int n = (int)((i / M) % N);
+        const int st = (int)(i / ((int64_t)M * N));
+        const int dir = st / tiles_s;
+        const int64_t row = (int64_t)(st % tiles_s) * M + m;
+        uint8_t v = 0;
+        if (row < ns) v = samples[row * N + (dir ? N - 1 - n : n)];
+        sigT[i] = v;
+    }
+}
+
+__global__ void samp_untranspose_kernel(const uint8_t* __restrict__ sampT, uint8_t* __restrict__ samples, int64_t ns, int N,
+                                        int M) {
+    const int64_t total = ns * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / N;
+        const int n = (int)(i % N);
+        samples[i] = sampT[((row / M) * N + n) * M + (row % M)];
+    }
+}
+
+// Diagonal TFIM energy, bit-exact with the reference's f64 accumulation order:
+//  chain   : e += v_i * (-Jz[i]) bond by bond                  1DTFIM/TrainingRNN_1DTFIM.py:31-38
+//  lattice : e += np.sum(v * (-Jz[i,:]), axis=1) for i<Nx-1, then e += np.sum(v * (-Jz[:,i]), axis=1) for i<Ny-1
+//            with NumPy's pairwise order inside np.sum       2DTFIM_2DRNN/Training2DRNN_2DTFIM.py:33-49
+__global__ void tfim_diag_kernel(const uint8_t* __restrict__ samples, int64_t ns, int N, int nx, int ny,
+                                 const double* __restrict__ jz, double* __restrict__ diag) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= ns) return;
+    const uint8_t* s = samples + b * N;
+    double e = 0.0;
+    if (nx <= 0) {
+        for (int i = 0; i < N - 1; ++i) {
+            const double v = s[i] == s[i + 1] ? 1.0 : -1.0;
+            e += v * (-jz[i]);
+        }
+    } else {
+        for (int i = 0; i < nx - 1; ++i) {
+            auto f = [&](int y) { return (s[i * ny + y] == s[(i + 1) * ny + y] ? 1.0 : -1.0) * (-jz[i * ny + y]); };
+            e += np_pairwise_sum(f, 0, ny);
+        }
+        for (int i = 0; i < ny - 1; ++i) {
+            auto f = [&](int x) { return (s[x * ny + i] == s[x * ny + i + 1] ? 1.0 : -1.0) * (-jz[x * ny + i]); };
+            e += np_pairwise_sum(f, 0, nx);
+        }
+    }
+    diag[b] = e;
+}
+
+// queue[slot][b][i]: slot 0 = sample, slot k+1 = site k flipped (1DTFIM/TrainingRNN_1DTFIM.py:40-48)
+__global__ void tfim_enumerate_kernel(const uint8_t* __restrict__ samples, int64_t ns, int N, int32_t* __restrict__ queue) {
+    const int64_t total = (int64_t)(N + 1) * ns * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int site = (int)(i % N);
+        const int64_t b = (i / N) % ns;
+        const int slot = (int)(i / ((int64_t)N * ns));
+        int v = samples[b * N + site];
+        if (slot > 0 && site == slot - 1) v = 1 - v;
+        queue[i] = v;
+    }
+}
+
+__device__ __forceinline__ double logaddexp_(double a, double b) {
+    const double mx = fmax(a, b), mn = fmin(a, b);
+    if (isinf(mx)) return mx;
+    return mx + log1p(exp(mn - mx));
+}
+
+// E_loc = diag - Bx * sum_k exp(0.5 * delta_k)      (1DTFIM/TrainingRNN_1DTFIM.py:74), summed in site order.
+// Parity model: P_sym = (P(s) + P(rev s))/2, the flip at site k appears at N-1-k in the reversed chain.
+__global__ void tfim_finalize_kernel(const double* __restrict__ diag, const double* __restrict__ delta,
+                                     const double* __restrict__ lp, int64_t ns, int N, int M, int tiles_s, double bx,
+                                     int parity, double* __restrict__ eloc, double* __restrict__ logp) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= ns) return;
+    const int64_t st = b / M;
+    const int m = (int)(b % M);
+    const double ln2 = 0.69314718055994530942;
+    double sum = 0.0, lpb;
+    if (!parity) {
+        lpb = lp[st * M + m];
+        if (bx != 0.0)
+            for (int k = 0; k < N; ++k) sum += exp(0.5 * delta[(st * N + k) * M + m]);
+    } else {
+        const int64_t st2 = st + tiles_s;
+        const double lp1 = lp[st * M + m], lp2 = lp[st2 * M + m];
+        lpb = logaddexp_(lp1, lp2) - ln2;
+        if (bx != 0.0)
+            for (int k = 0; k < N; ++k) {
+                const double a = lp1 + delta[(st * N + k) * M + m];
+                const double c = lp2 + delta[(st2 * N + (N - 1 - k)) * M + m];
+                sum += exp(0.5 * (logaddexp_(a, c) - ln2 - lpb));
+            }
+    }
+    eloc[b] = diag[b] - bx * sum;
+    if (logp) logp[b] = lpb;
+}
+
+__global__ void gather_logpsi_kernel(const double* __restrict__ lp_re, const double* __restrict__ lp_im, int64_t ns, int M,
+                                     int tiles_s, int parity, int complex_, double* __restrict__ out) {
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b >= ns) return;
+    const int64_t st = b / M;
+    const int m = (int)(b % M);
+    if (complex_) {
+        out[2 * b] = lp_re[st * M + m];
+        out[2 * b + 1] = lp_im[st * M + m];
+    } else if (parity) {
+        out[b] = logaddexp_(lp_re[st * M + m], lp_re[(st + tiles_s) * M + m]) - 0.69314718055994530942;
+    } else {
+        out[b] = lp_re[st * M + m];
+    }
+}
+
+// order of chain slots by decreasing length (sites re-run = N-1-s): merge the kinds by ascending s
+__global__ void chain_order_kernel(ChainPlan p, int* __restrict__ order) {
+    if (blockIdx.x || threadIdx.x) return;
+    int o = 0;
+    const int smax = max(p.n_kind0, max(p.n_kind1, p.n_kind2));
+    for (int s = 0; s < smax; ++s) {
+        if (s < p.n_kind0) order[o++] = s;
+        if (s < p.n_kind1) order[o++] = p.n_kind0 + s;
+        if (s < p.n_kind2) order[o++] = p.n_kind0 + p.n_kind1 + s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct GruWs {
+    T* pk;
+    uint8_t* sigT;
+    T* hstore;
+    double *la_sel, *la_oth, *ph_sel, *ph_oth, *delta_re, *delta_im, *lp_re, *lp_im, *diag;
+    int *counter, *order;
+};
+
+template <typename T>
+static GruWs<T> carve_gru(Ws& ws, const GruLayout& g, const GruLaunch& c, int64_t tiles, bool stash, int nslots, bool cplx,
+                          int64_t ns) {
+    GruWs<T> w;
+    memset(&w, 0, sizeof(w));
+    const size_t rows = (size_t)tiles * c.M;
+    w.pk = ws.take<T>(g.PK);
+    w.sigT = ws.take<uint8_t>(rows * g.N);
+    w.lp_re = ws.take<double>(rows);
+    w.lp_im = ws.take<double>(cplx ? rows : 0);
+    w.counter = ws.take<int>(4);
+    if (stash) {
+        w.hstore = ws.take<T>(rows * g.N * g.L * g.H);
+        w.la_sel = ws.take<double>(rows * g.N);
+        w.la_oth = ws.take<double>(rows * g.N);
+        if (cplx) {
+            w.ph_sel = ws.take<double>(rows * g.N);
+            w.ph_oth = ws.take<double>(rows * g.N);
+        }
+    }
+    if (nslots > 0) {
+        w.delta_re = ws.take<double>(rows * nslots);
+        if (cplx) w.delta_im = ws.take<double>(rows * nslots);
+        w.order = ws.take<int>(nslots);
+        w.diag = ws.take<double>((size_t)ns);
+    }
+    return w;
+}
+
+static inline int grid_for(int64_t n, int block = 256) { return (int)std::min<int64_t>(cdiv(n, block), 148 * 16); }
+
+template <typename K> static int set_smem(K kernel, int bytes) {
+    RNNWF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers (dispatch the bool template parameters)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool STASH, bool CPLX>
+static int launch_forward(const GruLayout& g, const GruLaunch& c, const GruWs<T>& w, int tiles, cudaStream_t s) {
+    const int block = c.NTc + kHeadThreads;
+    if (c.w_smem) {
+        auto k = gru_forward_kernel<T, true, STASH, CPLX>;
+        if (int e = set_smem(k, c.smem_bytes)) return e;
+        k<<<tiles, block, c.smem_bytes, s>>>(g, c, w.pk, w.sigT, w.lp_re, w.lp_im, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth);
+    } else {
+        auto k = gru_forward_kernel<T, false, STASH, CPLX>;
+        if (int e = set_smem(k, c.smem_bytes)) return e;
+        k<<<tiles, block, c.smem_bytes, s>>>(g, c, w.pk, w.sigT, w.lp_re, w.lp_im, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth);
+    }
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, bool CPLX>
+static int launch_chain(const GruLayout& g, const GruLaunch& c, const ChainPlan& plan, const GruWs<T>& w, cudaStream_t s) {
+    const int block = c.NTc + kHeadThreads;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<int64_t>((int64_t)plan.nslots * plan.tiles, sms);
+    RNNWF_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), s));
+    chain_order_kernel<<<1, 1, 0, s>>>(plan, w.order);
+    if (c.w_smem) {
+        auto k = gru_chain_kernel<T, true, CPLX>;
+        if (int e = set_smem(k, c.smem_bytes)) return e;
+        k<<<grid, block, c.smem_bytes, s>>>(g, c, plan, w.pk, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth, w.order,
+                                            w.delta_re, w.delta_im, w.counter);
+    } else {
+        auto k = gru_chain_kernel<T, false, CPLX>;
+        if (int e = set_smem(k, c.smem_bytes)) return e;
+        k<<<grid, block, c.smem_bytes, s>>>(g, c, plan, w.pk, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth, w.order,
+                                            w.delta_re, w.delta_im, w.counter);
+    }
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, bool CPLX>
+static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, uint8_t* sampT, int tiles, uint64_t seed,
+                         uint64_t off, cudaStream_t s) {
+    const int block = c.NTc + kHeadThreads;
+    if (c.w_smem) {
+        auto k = gru_sample_kernel<T, true, CPLX>;
+        if (int e = set_smem(k, c.smem_bytes)) return e;
+        k<<<tiles, block, c.smem_bytes, s>>>(g, c, pk, sampT, seed, off);
+    } else {
+        auto k = gru_sample_kernel<T, false, CPLX>;
+        if (int e = set_smem(k, c.smem_bytes)) return e;
+        k<<<tiles, block, c.smem_bytes, s>>>(g, c, pk, sampT, seed, off);
+    }
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// typed implementations behind the C ABI
+// ---------------------------------------------------------------------------------------------
+template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op, int64_t ns, int flags) {
+    const GruLayout g = make_gru_layout(m);
+    const GruLaunch c = choose_gru_launch<T>(g);
+    if (c.RT == 0) return 0;
+    const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
+    const int ndir = (flags & RNNWF_PARITY_SYM) ? 2 : 1;
+    const int64_t tiles = ndir * cdiv(ns, c.M);
+    Ws ws(nullptr, 0);
+    switch (op) {
+        case RNNWF_OP_SAMPLE:
+        case RNNWF_OP_LOGPSI: carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns); break;
+        case RNNWF_OP_TFIM_ELOC: carve_gru<T>(ws, g, c, tiles, true, g.N, cplx, ns); break;
+        case RNNWF_OP_J1J2_ELOC: carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns); ws.take<float>((size_t)ns * (2 * g.N + 1)); break;
+        case RNNWF_OP_VMC_GRAD: return gru_grad_workspace_bytes<T>(m, ns, flags);
+        default: return 0;
+    }
+    return ws.used + 256;
+}
+template size_t gru_workspace_bytes_t<float>(const rnnwf_model&, int, int64_t, int);
+template size_t gru_workspace_bytes_t<double>(const rnnwf_model&, int, int64_t, int);
+
+template <typename T>
+int gru_sample_t(const rnnwf_model& m, const void* params, int64_t ns, uint64_t seed, uint64_t off, uint8_t* out, void* wsp,
+                 size_t wsb, cudaStream_t s) {
+    const GruLayout g = make_gru_layout(m);
+    const GruLaunch c = choose_gru_launch<T>(g);
+    RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
+    const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
+    const int tiles = (int)cdiv(ns, c.M);
+    Ws ws(wsp, wsb);
+    GruWs<T> w = carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns);
+    RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
+    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
+    int e = cplx ? launch_sample<T, true>(g, c, w.pk, w.sigT, tiles, seed, off, s)
+                 : launch_sample<T, false>(g, c, w.pk, w.sigT, tiles, seed, off, s);
+    if (e) return e;
+    samp_untranspose_kernel<<<grid_for(ns * g.N), 256, 0, s>>>(w.sigT, out, ns, g.N, c.M);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+template int gru_sample_t<float>(const rnnwf_model&, const void*, int64_t, uint64_t, uint64_t, uint8_t*, void*, size_t, cudaStream_t);
+template int gru_sample_t<double>(const rnnwf_model&, const void*, int64_t, uint64_t, uint64_t, uint8_t*, void*, size_t, cudaStream_t);
+
+template <typename T>
+int gru_logpsi_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, int flags, double* out, void* wsp,
+                 size_t wsb, cudaStream_t s) {
+    const GruLayout g = make_gru_layout(m);
+    const GruLaunch c = choose_gru_launch<T>(g);
+    RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
+    const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
+    const int parity = (flags & RNNWF_PARITY_SYM) ? 1 : 0;
+    RNNWF_CHECK(!(cplx && parity), -2, "parity symmetry is only defined for the probability head");
+    const int tiles_s = (int)cdiv(ns, c.M), ndir = parity ? 2 : 1, tiles = tiles_s * ndir;
+    Ws ws(wsp, wsb);
+    GruWs<T> w = carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns);
+    RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
+    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
+    sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
+    int e = cplx ? launch_forward<T, false, true>(g, c, w, tiles, s) : launch_forward<T, false, false>(g, c, w, tiles, s);
+    if (e) return e;
+    gather_logpsi_kernel<<<grid_for(ns), 256, 0, s>>>(w.lp_re, w.lp_im, ns, c.M, tiles_s, parity, cplx, out);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+template int gru_logpsi_t<float>(const rnnwf_model&, const void*, const uint8_t*, int64_t, int, double*, void*, size_t, cudaStream_t);
+template int gru_logpsi_t<double>(const rnnwf_model&, const void*, const uint8_t*, int64_t, int, double*, void*, size_t, cudaStream_t);
+
+template <typename T>
+int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, const double* jz, double bx,
+                    int flags, double* eloc, double* logp, void* wsp, size_t wsb, cudaStream_t s) {
+    const GruLayout g = make_gru_layout(m);
+    const GruLaunch c = choose_gru_launch<T>(g);
+    RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
+    RNNWF_CHECK(m.head == RNNWF_HEAD_PROB, -2, "TFIM local energies need the probability head");
+    const int parity = (flags & RNNWF_PARITY_SYM) ? 1 : 0;
+    const int tiles_s = (int)cdiv(ns, c.M), ndir = parity ? 2 : 1, tiles = tiles_s * ndir;
+    Ws ws(wsp, wsb);
+    GruWs<T> w = carve_gru<T>(ws, g, c, tiles, true, g.N, false, ns);
+    RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
+    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
+    sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
+    tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
+    if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
+        if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
+        ChainPlan plan{g.N, g.N, 0, 0, tiles};
+        if (int e = launch_chain<T, false>(g, c, plan, w, s)) return e;
+    } else {
+        if (int e = launch_forward<T, false, false>(g, c, w, tiles, s)) return e;
+    }
+    tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(w.diag, w.delta_re, w.lp_re, ns, g.N, c.M, tiles_s, bx, parity, eloc, logp);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+template int gru_tfim_eloc_t<float>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, double, int, double*,
+                                    double*, void*, size_t, cudaStream_t);
+template int gru_tfim_eloc_t<double>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, double, int, double*,
+                                     double*, void*, size_t, cudaStream_t);
+
+int tfim_diag_impl(const rnnwf_model& m, const uint8_t* samples, int64_t ns, const double* jz, double* diag, cudaStream_t s) {
+    tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, m.n_sites, m.nx, m.ny, jz, diag);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int tfim_enumerate_impl(const uint8_t* samples, int64_t ns, int N, int32_t* queue, cudaStream_t s) {
+    tfim_enumerate_kernel<<<grid_for((int64_t)(N + 1) * ns * N), 256, 0, s>>>(samples, ns, N, queue);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rnnwf

@@ -1,0 +1,50 @@
+// host_util.cuh — workspace bump allocator and launch-geometry selection (host side).
+#pragma once
+#include "gru_engine.cuh"
+
+namespace rnnwf {
+
+// Bump allocator over the caller-provided workspace.  With base == nullptr it only measures.
+struct Ws {
+    unsigned char* base;
+    size_t used;
+    size_t cap;
+    Ws(void* p, size_t c) : base(reinterpret_cast<unsigned char*>(p)), used(0), cap(c) {}
+    template <typename U> U* take(size_t n) {
+        used = (used + 255) & ~(size_t)255;
+        U* r = base ? reinterpret_cast<U*>(base + used) : nullptr;
+        used += n * sizeof(U);
+        return r;
+    }
+    bool ok() const { return base == nullptr || used <= cap; }
+};
+
+// Pick (RT, M) so that CT*RT fills whole groups of 4 warps (one per SM sub-partition) as tightly as
+// possible, the hidden-state tile + resident weights fit in 227 KB of shared memory, and M is as large
+// as possible among near-ties.  Block = compute threads (<= 384) + 4 head warps.
+template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g) {
+    constexpr int SPT = VT<T>::SPT;
+    GruLaunch best;
+    memset(&best, 0, sizeof(best));
+    for (int wsm = 1; wsm >= 0; --wsm) {
+        double best_eff = -1.0;
+        for (int RT = 1; RT <= 64; ++RT) {
+            const int nt = g.CT * RT, M = RT * SPT;
+            if (nt > 384 || M > 2 * kHeadThreads) break;
+            const int Mp = (M + 15) & ~15;
+            size_t smem = (wsm ? (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) : 0) + (size_t)g.L * g.H * M * sizeof(T) +
+                          2 * (size_t)Mp + 64;
+            if (smem > (size_t)kSmemLimit) break;
+            const double eff = (double)nt / (128.0 * (double)((nt + 127) / 128));
+            if (eff >= best_eff - 0.03) {   // near-tie: prefer the larger tile
+                if (eff > best_eff) best_eff = eff;
+                best.CT = g.CT; best.RT = RT; best.M = M; best.Mp = Mp;
+                best.NTc = (nt + 31) & ~31; best.w_smem = wsm; best.smem_bytes = (int)smem;
+            }
+        }
+        if (best.RT > 0) return best;
+    }
+    return best;
+}
+
+}  // namespace rnnwf

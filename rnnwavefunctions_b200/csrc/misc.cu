@@ -1,0 +1,65 @@
+// misc.cu — TF1 Adam update and energy moments.
+#include "api_internal.h"
+
+namespace rnnwf {
+
+// tf.train.AdamOptimizer.apply_gradients (1DTFIM/TrainingRNN_1DTFIM.py:113,164):
+//   lr_t = lr sqrt(1-b2^t)/(1-b1^t);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  theta -= lr_t m/(sqrt(v)+eps)
+template <typename T>
+__global__ void adam_kernel(int64_t n, T* __restrict__ theta, T* __restrict__ mom, T* __restrict__ vel,
+                            const double* __restrict__ grad, double gs, double lr_t, double b1, double b2, double eps) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T g = (T)(grad[i] * gs);
+        const T m = (T)b1 * mom[i] + (T)(1.0 - b1) * g;
+        const T v = (T)b2 * vel[i] + (T)(1.0 - b2) * g * g;
+        mom[i] = m;
+        vel[i] = v;
+        theta[i] = theta[i] - (T)lr_t * m / (sqrt(v) + (T)eps);
+    }
+}
+
+int adam_step_impl(int dtype, int64_t n, void* theta, void* mom, void* vel, const double* grad, double gs, double lr, double b1,
+                   double b2, double eps, int64_t t, cudaStream_t s) {
+    const double lr_t = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
+    const int grid = (int)std::min<int64_t>(cdiv(n, 256), 1184);
+    if (dtype == RNNWF_F32)
+        adam_kernel<float><<<grid, 256, 0, s>>>(n, (float*)theta, (float*)mom, (float*)vel, grad, gs, lr_t, b1, b2, eps);
+    else
+        adam_kernel<double><<<grid, 256, 0, s>>>(n, (double*)theta, (double*)mom, (double*)vel, grad, gs, lr_t, b1, b2, eps);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// stats = {sum E, sum E^2, n}; single block, fixed summation order (deterministic).
+__global__ void moments_kernel(const double* __restrict__ e, int64_t ns, int stride, double* __restrict__ stats) {
+    __shared__ double s1[256], s2[256];
+    double a = 0.0, b = 0.0;
+    for (int64_t i = threadIdx.x; i < ns; i += blockDim.x) {
+        const double v = e[i * stride];
+        a += v;
+        b += v * v;
+    }
+    s1[threadIdx.x] = a;
+    s2[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+            s2[threadIdx.x] += s2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats[0] = s1[0];
+        stats[1] = s2[0];
+        stats[2] = (double)ns;
+    }
+}
+
+int energy_moments_impl(const double* eloc, int64_t ns, int stride, double* stats, cudaStream_t s) {
+    moments_kernel<<<1, 256, 0, s>>>(eloc, ns, stride, stats);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace rnnwf

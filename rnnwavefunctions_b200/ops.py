@@ -1,0 +1,184 @@
+"""Torch-tensor level wrappers over the C ABI (device pointers in, device tensors out).
+
+PyTorch is plumbing here: it owns device memory and streams.  All arithmetic happens in librnnwf_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (CELL_GRU, CELL_MDRNN, F32, F64, HEAD_COMPLEX, HEAD_PROB, OP_J1J2_ELOC, OP_LOGPSI, OP_SAMPLE,
+                   OP_TFIM_ELOC, OP_VMC_GRAD, PARITY_SYM, Model, check)
+
+
+def make_model(cell=CELL_GRU, head=HEAD_PROB, dtype=F32, num_layers=1, units=10, n_sites=1, nx=0, ny=0) -> Model:
+    return Model(cell, head, dtype, num_layers, units, n_sites, nx, ny)
+
+
+def torch_dtype(model: Model):
+    return torch.float32 if model.dtype == F32 else torch.float64
+
+
+def param_count(model: Model) -> int:
+    n = _lib.load().rnnwf_param_count(C.byref(model))
+    if n < 0:
+        check(-1)
+    return int(n)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _Workspace:
+    """Grow-only device scratch buffer per device (the library itself keeps no device state)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, nbytes: int, device):
+        key = str(device)
+        b = self.buf.get(key)
+        if b is None or b.numel() < nbytes:
+            self.buf.pop(key, None)
+            b = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self.buf[key] = b
+        return b
+
+
+_WS = _Workspace()
+
+
+def release_workspace():
+    _WS.buf.clear()
+
+
+def _ws_for(model, op, ns, flags, device):
+    n = _lib.load().rnnwf_workspace_bytes(C.byref(model), op, ns, flags)
+    if n == 0:
+        raise _lib.RnnwfError(f"workspace query failed for op {op}: {_lib.load().rnnwf_last_error().decode()}")
+    return _WS.get(n, device), n
+
+
+def _check_params(model, params):
+    if not params.is_cuda or params.dtype != torch_dtype(model) or not params.is_contiguous():
+        raise ValueError("params must be a contiguous CUDA tensor of the model dtype")
+    if params.numel() != param_count(model):
+        raise ValueError(f"params has {params.numel()} entries, model needs {param_count(model)}")
+
+
+def as_u8_samples(samples, device, n_sites):
+    """Accept numpy / torch integer samples of any int dtype and [ns, N] or [ns, Nx, Ny] shape."""
+    t = torch.as_tensor(samples)
+    t = t.reshape(t.shape[0], -1)
+    if t.shape[1] != n_sites:
+        raise ValueError(f"samples have {t.shape[1]} sites, model has {n_sites}")
+    return t.to(device=device, dtype=torch.uint8, non_blocking=True).contiguous()
+
+
+def sample(model, params, ns, seed=0, sample_offset=0):
+    """-> uint8 [ns, N] on params.device."""
+    _check_params(model, params)
+    ws, nb = _ws_for(model, OP_SAMPLE, ns, 0, params.device)
+    out = torch.empty((ns, model.n_sites), dtype=torch.uint8, device=params.device)
+    check(_lib.load().rnnwf_sample(C.byref(model), _ptr(params), ns, seed & (2**64 - 1), sample_offset, _ptr(out), _ptr(ws), nb,
+                                   _stream()))
+    return out
+
+
+def logpsi(model, params, samples_u8, flags=0):
+    """-> float64 [ns] (probability head) or complex128 [ns] (complex head)."""
+    _check_params(model, params)
+    ns = samples_u8.shape[0]
+    ws, nb = _ws_for(model, OP_LOGPSI, ns, flags, params.device)
+    cplx = model.head == HEAD_COMPLEX
+    out = torch.empty((ns, 2) if cplx else (ns,), dtype=torch.float64, device=params.device)
+    check(_lib.load().rnnwf_logpsi(C.byref(model), _ptr(params), _ptr(samples_u8), ns, flags, _ptr(out), _ptr(ws), nb, _stream()))
+    return torch.view_as_complex(out) if cplx else out
+
+
+def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
+    _check_params(model, params)
+    ns = samples_u8.shape[0]
+    ws, nb = _ws_for(model, OP_TFIM_ELOC, ns, flags, params.device)
+    jz = torch.as_tensor(jz, dtype=torch.float64).reshape(-1).to(params.device).contiguous()
+    eloc = torch.empty(ns, dtype=torch.float64, device=params.device)
+    logp = torch.empty(ns, dtype=torch.float64, device=params.device) if want_logp else None
+    check(_lib.load().rnnwf_tfim_eloc(C.byref(model), _ptr(params), _ptr(samples_u8), ns, _ptr(jz), float(bx), flags, _ptr(eloc),
+                                      _ptr(logp), _ptr(ws), nb, _stream()))
+    return eloc, logp
+
+
+def tfim_diag(model, samples_u8, jz):
+    ns = samples_u8.shape[0]
+    jz = torch.as_tensor(jz, dtype=torch.float64).reshape(-1).to(samples_u8.device).contiguous()
+    out = torch.empty(ns, dtype=torch.float64, device=samples_u8.device)
+    check(_lib.load().rnnwf_tfim_diag(C.byref(model), _ptr(samples_u8), ns, _ptr(jz), _ptr(out), _stream()))
+    return out
+
+
+def tfim_enumerate(samples_u8):
+    ns, N = samples_u8.shape
+    out = torch.empty((N + 1, ns, N), dtype=torch.int32, device=samples_u8.device)
+    check(_lib.load().rnnwf_tfim_enumerate(_ptr(samples_u8), ns, N, _ptr(out), _stream()))
+    return out
+
+
+def j1j2_enumerate(samples_u8, j1, j2, bz, periodic=False, marshall_sign=False, want_sigmas=True):
+    ns, N = samples_u8.shape
+    dev = samples_u8.device
+    j1, j2, bz = (torch.as_tensor(a, dtype=torch.float64).to(dev).contiguous() for a in (j1, j2, bz))
+    rows = 2 * N + 1
+    sig = torch.zeros((ns, rows, N), dtype=torch.int32, device=dev) if want_sigmas else None
+    el = torch.zeros((ns, rows), dtype=torch.float32, device=dev)
+    cnt = torch.zeros(ns, dtype=torch.int32, device=dev)
+    check(_lib.load().rnnwf_j1j2_enumerate(_ptr(samples_u8), ns, N, _ptr(j1), _ptr(j2), _ptr(bz), int(periodic), int(marshall_sign),
+                                           _ptr(sig), _ptr(el), _ptr(cnt), _stream()))
+    return sig, el, cnt
+
+
+def j1j2_eloc(model, params, samples_u8, j1, j2, bz, marshall_sign=False, want_logpsi=True):
+    _check_params(model, params)
+    ns = samples_u8.shape[0]
+    dev = params.device
+    ws, nb = _ws_for(model, OP_J1J2_ELOC, ns, 0, dev)
+    j1, j2, bz = (torch.as_tensor(a, dtype=torch.float64).to(dev).contiguous() for a in (j1, j2, bz))
+    eloc = torch.empty((ns, 2), dtype=torch.float64, device=dev)
+    lpsi = torch.empty((ns, 2), dtype=torch.float64, device=dev) if want_logpsi else None
+    check(_lib.load().rnnwf_j1j2_eloc(C.byref(model), _ptr(params), _ptr(samples_u8), ns, _ptr(j1), _ptr(j2), _ptr(bz),
+                                      int(marshall_sign), _ptr(eloc), _ptr(lpsi), _ptr(ws), nb, _stream()))
+    return torch.view_as_complex(eloc), (torch.view_as_complex(lpsi) if want_logpsi else None)
+
+
+def vmc_grad(model, params, samples_u8, weights, flags=0):
+    """weights: float64 [ns] (probability head) or complex128 / float64 [ns,2] (complex head). -> float64 [P]."""
+    _check_params(model, params)
+    ns = samples_u8.shape[0]
+    ws, nb = _ws_for(model, OP_VMC_GRAD, ns, flags, params.device)
+    w = weights
+    if w.is_complex():
+        w = torch.view_as_real(w.to(torch.complex128))
+    w = w.to(device=params.device, dtype=torch.float64).contiguous()
+    grad = torch.empty(param_count(model), dtype=torch.float64, device=params.device)
+    check(_lib.load().rnnwf_vmc_grad(C.byref(model), _ptr(params), _ptr(samples_u8), ns, _ptr(w), flags, _ptr(grad), _ptr(ws), nb,
+                                     _stream()))
+    return grad
+
+
+def adam_step(model, theta, mom, vel, grad, t, lr, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
+    check(_lib.load().rnnwf_adam_step(model.dtype, theta.numel(), _ptr(theta), _ptr(mom), _ptr(vel), _ptr(grad), float(grad_scale),
+                                      float(lr), beta1, beta2, eps, int(t), _stream()))
+
+
+def energy_moments(eloc_f64, stride=1):
+    ns = eloc_f64.numel() // stride
+    out = torch.empty(3, dtype=torch.float64, device=eloc_f64.device)
+    check(_lib.load().rnnwf_energy_moments(_ptr(eloc_f64), ns, stride, _ptr(out), _stream()))
+    return out

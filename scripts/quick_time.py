@@ -1,0 +1,40 @@
+"""Quick device timing of the cfg2 stages (not the bench contract; used while developing)."""
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, ".")
+from rnnwavefunctions_b200 import ops, params as P
+
+ns = int(sys.argv[1]) if len(sys.argv) > 1 else 1200
+N, L, H = 1000, 3, 50
+dev = torch.device("cuda:0")
+model = ops.make_model(num_layers=L, units=H, n_sites=N)
+flat = torch.tensor(P.init_flat(P.gru_shapes([H] * L), 111, np.float32), device=dev)
+Jz = np.ones(N)
+
+
+def timed(fn, reps=1):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        r = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps, r
+
+
+t, s = timed(lambda: ops.sample(model, flat, ns, seed=1))
+t, s = timed(lambda: ops.sample(model, flat, ns, seed=1))
+print(f"sample  ns={ns}: {t:.1f} ms  mean spin {s.float().mean().item():.3f}")
+t, lp = timed(lambda: ops.logpsi(model, flat, s))
+t, lp = timed(lambda: ops.logpsi(model, flat, s))
+print(f"logpsi  ns={ns}: {t:.1f} ms  mean lp {lp.mean().item():.3f}")
+t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
+F = 75800.0
+steps = ns * N * (N + 1) / 2
+print(f"eloc    ns={ns}: {t:.1f} ms  mean E {e.mean().item():.3f}  -> {steps * F / t / 1e9:.2f} TFLOP/s algorithmic, "
+      f"{ns / t * 1e3:.1f} samples/s")
