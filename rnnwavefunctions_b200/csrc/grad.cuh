@@ -1,0 +1,579 @@
+// grad.cuh — K3: VMC gradient  sum_s [ w_re[s] d Re log psi_s + w_im[s] d Im log psi_s ]  by BPTT.
+//
+// Replaces optimizer.compute_gradients(cost) (1DTFIM/TrainingRNN_1DTFIM.py:156-160; complex form
+// J1J2/TrainingRNN_J1J2.py:197-201).  Structure:
+//   1. teacher-forced base pass with stash (gru_forward_kernel<STASH>): every layer's state per site.
+//   2. for layer l = L-1 .. 0: gru_bwd_layer_kernel walks the sites backwards on a tile of M samples,
+//      recomputes the gates from the stashed states, propagates d h through time (registers) and to the
+//      layer below (dxbuf in HBM), and writes the gate gradients G = [da_r, da_u, da_c, dq] to HBM.
+//   3. wgrad_kernel: split-K reduction  dW = sum_{sample,site} [x; h_prev; 1]^T G  with FP32 FMAs per
+//      (tile, site) block and FP64 accumulation across blocks (deterministic; no atomics).
+// Included at the end of gru.cu (same translation unit as the forward launchers).
+#pragma once
+#include "gru_kernels.cuh"
+#include "host_util.cuh"
+
+namespace rnnwf {
+
+struct BwdLaunch {
+    int CT, RT, M, Mp, NT, w_smem, smem_bytes;
+};
+
+struct GruLayoutT {   // transposed packed weights for the backward GEMMs
+    int off_h[kMaxLayers], off_x[kMaxLayers], total;
+};
+
+inline GruLayoutT make_gru_layout_T(const GruLayout& g) {
+    GruLayoutT t;
+    memset(&t, 0, sizeof(t));
+    int o = 0;
+    for (int l = 0; l < g.L; ++l) {
+        t.off_h[l] = o;
+        o += align4(3 * g.H * g.CT * 2);
+        t.off_x[l] = o;
+        if (l > 0) o += align4(3 * g.H * g.CT * 2);
+    }
+    t.total = o;
+    return t;
+}
+
+// WT_h[(gate*H + j)][ct][u] = W_h,gate[i = 2ct+u][j]   (gate 0:r, 1:u from Kg rows d.., 2: Kch)
+// WT_x[(gate*H + j)][ct][u] = W_x,gate[i = 2ct+u][j]   (gate 0:r, 1:u from Kg rows 0..d-1, 2: Kci)
+template <typename T>
+__global__ void pack_gru_T_kernel(GruLayout g, GruLayoutT t, const T* __restrict__ flat, T* __restrict__ pkT) {
+    const int H = g.H, CT = g.CT;
+    const int per = 3 * H * CT * 2;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < t.total; idx += gridDim.x * blockDim.x) {
+        int l = 0;
+        while (l + 1 < g.L && idx >= t.off_h[l + 1]) ++l;
+        const int d = g.d[l];
+        const T* Kg = flat + g.flat_off[l];
+        const T* Kci = Kg + (d + H) * 2 * H + 2 * H;
+        const T* Kch = Kci + d * H;
+        T val = T(0);
+        int loc = idx - t.off_h[l];
+        const bool xpart = l > 0 && idx >= t.off_x[l];
+        if (xpart) loc = idx - t.off_x[l];
+        if (loc < per) {
+            const int u = loc & 1, ct = (loc >> 1) % CT, kk = (loc >> 1) / CT, gate = kk / H, j = kk % H, i = 2 * ct + u;
+            if (!xpart) {
+                if (i < H) val = gate == 0 ? Kg[(d + i) * 2 * H + j] : gate == 1 ? Kg[(d + i) * 2 * H + H + j] : Kch[i * H + j];
+            } else {
+                if (i < d) val = gate == 0 ? Kg[i * 2 * H + j] : gate == 1 ? Kg[i * 2 * H + H + j] : Kci[i * H + j];
+            }
+        }
+        pkT[idx] = val;
+    }
+}
+
+// per-row weights: PROB: roww[R] = w[s] (parity: split between the two directions by their share of P_sym)
+//                  COMPLEX: roww[R] = w_re[s], roww[rows + R] = w_im[s]
+__global__ void row_weight_kernel(const double* __restrict__ w, const double* __restrict__ lp, int64_t ns, int M, int tiles_s,
+                                  int parity, int cplx, double* __restrict__ roww) {
+    const int64_t rows_dir = (int64_t)tiles_s * M;
+    const int ndir = parity ? 2 : 1;
+    const int64_t rows = rows_dir * ndir;
+    for (int64_t R = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; R < rows; R += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = R % rows_dir;
+        double a = 0.0, b = 0.0;
+        if (s < ns) {
+            if (cplx) { a = w[2 * s]; b = w[2 * s + 1]; }
+            else if (!parity) a = w[s];
+            else {
+                const double l_this = lp[R], l_other = lp[R < rows_dir ? R + rows_dir : R - rows_dir];
+                a = w[s] / (1.0 + exp(l_other - l_this));
+            }
+        }
+        roww[R] = a;
+        if (cplx) roww[rows + R] = b;
+    }
+}
+
+template <typename T, bool WSMEM, bool CPLX>
+__global__ void __launch_bounds__(384, 1)
+gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __restrict__ pk, const T* __restrict__ pkT,
+                     const uint8_t* __restrict__ sigT, const T* __restrict__ hstore, const double* __restrict__ la_sel,
+                     const double* __restrict__ la_oth, const double* __restrict__ ph_sel, const double* __restrict__ roww,
+                     int64_t rows_total, T* __restrict__ dxbuf, T* __restrict__ Gbuf, T* __restrict__ dzbuf) {
+    constexpr int SPT = VT<T>::SPT;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, H = g.H, CT = g.CT, L = g.L, N = g.N, M = c.M, d = g.d[l];
+    const bool top = l == L - 1;
+    const int per = align4(3 * H * CT * 2);
+    size_t off = 0;
+    const T* wl;
+    const T *WTh, *WTx = nullptr;
+    if (WSMEM) {
+        T* wsm = reinterpret_cast<T*>(smem);
+        const T* src = pk + g.pk_off[l];
+        for (int i = tid; i < g.pk_size[l]; i += blockDim.x) wsm[i] = src[i];
+        wl = wsm;
+        T* th = wsm + g.pk_size[l];
+        for (int i = tid; i < per; i += blockDim.x) th[i] = pkT[gt.off_h[l] + i];
+        WTh = th;
+        int words = g.pk_size[l] + per;
+        if (l > 0) {
+            T* tx = th + per;
+            for (int i = tid; i < per; i += blockDim.x) tx[i] = pkT[gt.off_x[l] + i];
+            WTx = tx;
+            words += per;
+        }
+        off = ((size_t)words * sizeof(T) + 15) & ~(size_t)15;
+    } else {
+        wl = pk + g.pk_off[l];
+        WTh = pkT + gt.off_h[l];
+        if (l > 0) WTx = pkT + gt.off_x[l];
+    }
+    T* xs = reinterpret_cast<T*>(smem + off);
+    off += (size_t)(l > 0 ? d : 0) * M * sizeof(T);
+    T* hp = reinterpret_cast<T*>(smem + off);
+    off += (size_t)H * M * sizeof(T);
+    T* G = reinterpret_cast<T*>(smem + off);
+    off += (size_t)4 * H * M * sizeof(T);
+    T* dz = reinterpret_cast<T*>(smem + off);
+    off += (size_t)4 * M * sizeof(T);
+    uint8_t* codes = smem + off;
+
+    const bool is_compute = tid < CT * c.RT;
+    const int ct = tid % CT, rt = tid / CT, row0 = rt * SPT;
+    const int st = blockIdx.x;
+    constexpr int NZ = CPLX ? 4 : 2;
+    // head weights of this thread's two units (top layer only)
+    T wd[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    if (top && is_compute) {
+        const T* hw = pk + g.pk_head;
+        for (int u = 0; u < 2; ++u) {
+            const int j = 2 * ct + u;
+            if (j < H) {
+                wd[u][0] = hw[2 * j]; wd[u][1] = hw[2 * j + 1];
+                if (CPLX) { wd[u][2] = hw[2 * H + 2 + 2 * j]; wd[u][3] = hw[2 * H + 2 + 2 * j + 1]; }
+            }
+        }
+    }
+    T carry[2][SPT];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) carry[u][s] = T(0);
+    __syncthreads();
+
+    for (int n = N - 1; n >= 0; --n) {
+        const size_t blk = (size_t)st * N + n;
+        {   // (a) stage the inputs of site n:  h_prev = h^l_{n-1},  x = h^{l-1}_n  (or the one-hot code of sigma_{n-1})
+            const T* hsrc = n > 0 ? hstore + ((blk - 1) * L + l) * H * M : nullptr;
+            for (int i = tid; i < H * M; i += blockDim.x) hp[i] = hsrc ? hsrc[i] : T(0);
+            if (l > 0) {
+                const T* xsrc = hstore + (blk * L + (l - 1)) * H * M;
+                for (int i = tid; i < d * M; i += blockDim.x) xs[i] = xsrc[i];
+            } else {
+                for (int m = tid; m < M; m += blockDim.x) codes[m] = n > 0 ? sigT[(blk - 1) * M + m] : (uint8_t)2;
+            }
+            if (top) {
+                for (int m = tid; m < M; m += blockDim.x) {
+                    const int sg = sigT[blk * M + m];
+                    const double lo = la_oth[blk * M + m];
+                    const double wre = roww[(size_t)st * M + m];
+                    T z[4] = {0, 0, 0, 0};
+                    if (!CPLX) {
+                        const double t = wre * exp(lo);        // w (1 - p_sel) = w p_oth
+                        z[sg] = (T)t;
+                        z[1 - sg] = (T)(-t);
+                    } else {
+                        const double t = 0.5 * wre * exp(2.0 * lo);   // d(1/2 log p_sel)/dz ; 0 when the other outcome is masked
+                        z[sg] = (T)t;
+                        z[1 - sg] = (T)(-t);
+                        const double y = fabs(ph_sel[blk * M + m]) / kPi;
+                        z[2 + sg] = (T)(roww[rows_total + (size_t)st * M + m] * kPi * (1.0 - y) * (1.0 - y));
+                    }
+#pragma unroll
+                    for (int o = 0; o < NZ; ++o) {
+                        dz[o * M + m] = z[o];
+                        dzbuf[(blk * NZ + o) * M + m] = z[o];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        T cdir[2][SPT];
+        if (is_compute) {   // (c) recompute gates, local backward, publish gate gradients
+            T ar[2][SPT], au[2][SPT], ac[2][SPT], aq[2][SPT];
+            gru_preact<T>(g, l, wl, l == 0 ? nullptr : xs, hp, codes, M, ct, rt, ar, au, ac, aq);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * ct + u;
+                if (j < H) {
+                    T hold[SPT], dout[SPT], g0[SPT], g1[SPT], g2[SPT], g3[SPT];
+                    ldv<SPT>(hold, hp + j * M + row0);
+                    if (top) {
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            T v = dz[row0 + s] * wd[u][0] + dz[M + row0 + s] * wd[u][1];
+                            if (CPLX) v += dz[2 * M + row0 + s] * wd[u][2] + dz[3 * M + row0 + s] * wd[u][3];
+                            dout[s] = v;
+                        }
+                    } else {
+                        ldv<SPT>(dout, dxbuf + (blk * H + j) * M + row0);
+                    }
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        const T r = sigmoid_(ar[u][s]);
+                        const T uu = sigmoid_(au[u][s]);
+                        const T q = aq[u][s];
+                        const T cc = tanh_(fma(r, q, ac[u][s]));
+                        const T dh = carry[u][s] + dout[s];
+                        const T dcc = dh * (T(1) - uu);
+                        const T duu = dh * (hold[s] - cc);
+                        cdir[u][s] = dh * uu;
+                        const T dac = dcc * (T(1) - cc * cc);
+                        g0[s] = dac * q * r * (T(1) - r);
+                        g1[s] = duu * uu * (T(1) - uu);
+                        g2[s] = dac;
+                        g3[s] = dac * r;
+                    }
+                    stv<SPT>(G + (0 * H + j) * M + row0, g0);
+                    stv<SPT>(G + (1 * H + j) * M + row0, g1);
+                    stv<SPT>(G + (2 * H + j) * M + row0, g2);
+                    stv<SPT>(G + (3 * H + j) * M + row0, g3);
+                    T* gb = Gbuf + blk * 4 * H * M;
+                    stv<SPT>(gb + (0 * H + j) * M + row0, g0);
+                    stv<SPT>(gb + (1 * H + j) * M + row0, g1);
+                    stv<SPT>(gb + (2 * H + j) * M + row0, g2);
+                    stv<SPT>(gb + (3 * H + j) * M + row0, g3);
+                }
+            }
+        }
+        __syncthreads();
+        if (is_compute) {   // (e) d h_{n-1} and d x through the transposed weights
+            T accH[2][SPT], accX[2][SPT];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) { accH[u][s] = T(0); accX[u][s] = T(0); }
+            for (int gate = 0; gate < 3; ++gate) {
+                const T* Gh = G + (gate == 2 ? 3 : gate) * H * M + row0;
+                const T* Gx = G + gate * H * M + row0;
+                const T* wh = WTh + (size_t)gate * H * CT * 2 + ct * 2;
+                const T* wx = l > 0 ? WTx + (size_t)gate * H * CT * 2 + ct * 2 : nullptr;
+#pragma unroll 2
+                for (int j = 0; j < H; ++j) {
+                    T a[SPT], w[2];
+                    ldv<SPT>(a, Gh + j * M);
+                    ldv<2>(w, wh + j * CT * 2);
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        accH[0][s] = fma(a[s], w[0], accH[0][s]);
+                        accH[1][s] = fma(a[s], w[1], accH[1][s]);
+                    }
+                    if (l > 0) {
+                        T b[SPT], v[2];
+                        if (gate == 2) ldv<SPT>(b, Gx + j * M);
+                        ldv<2>(v, wx + j * CT * 2);
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            const T bb = gate == 2 ? b[s] : a[s];
+                            accX[0][s] = fma(bb, v[0], accX[0][s]);
+                            accX[1][s] = fma(bb, v[1], accX[1][s]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int j = 2 * ct + u;
+                if (j < H) {
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) carry[u][s] = cdir[u][s] + accH[u][s];
+                    if (l > 0 && j < d) stv<SPT>(dxbuf + (blk * H + j) * M + row0, accX[u]);
+                }
+            }
+        }
+        // next iteration's (a) only writes xs/hp/dz/codes, which nobody reads in (e); the barrier after (a)
+        // orders (e) before the next (c) rewrites G.
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// split-K weight-gradient reduction:  C[r][c] = sum_{blk} sum_m A[blk][r][m] * B[blk][c][m]
+//   A rows: [x rows (rows0) | h rows (rows1) | ones],  B = gate gradients (cols) of the same (tile, site)
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct WgradArgs {
+    const T* hstore;       // [blk][L][H][M]
+    const uint8_t* sigT;   // [blk][M]
+    const T* B;            // [blk][cols][M]
+    int L, H, M, N;
+    int xmode;             // 0: no x rows, 1: x = hstore layer lx of the same block, 2: one-hot of sigma_{n-1}
+    int lx, rows0;
+    int lh, hshift, rows1; // h rows: hstore layer lh of block (blk - hshift), zero at n == 0 when hshift
+    int cols;
+    int64_t nblk;
+    int ksplit, rtiles, ctiles;
+};
+
+constexpr int kWgTile = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs<T> a, double* __restrict__ partial) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int M = a.M, MS = M + 4;
+    T* As = reinterpret_cast<T*>(smem);
+    T* Bs = As + kWgTile * MS;
+    const int tile = blockIdx.x, ks = blockIdx.y;
+    const int r0 = (tile / a.ctiles) * kWgTile, c0 = (tile % a.ctiles) * kWgTile;
+    const int R = a.rows0 + a.rows1 + 1;
+    const int tc = threadIdx.x % 16, tr = threadIdx.x / 16;
+    const int64_t b0 = a.nblk * ks / a.ksplit, b1 = a.nblk * (ks + 1) / a.ksplit;
+    double accd[4][4];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) accd[i][j] = 0.0;
+    for (int64_t blk = b0; blk < b1; ++blk) {
+        const int n = (int)(blk % a.N);
+        for (int i = threadIdx.x; i < kWgTile * (M / 4); i += blockDim.x) {
+            const int row = i / (M / 4), m4 = (i % (M / 4)) * 4;
+            const int r = r0 + row, cc = c0 + row;
+            T va[4] = {0, 0, 0, 0}, vb[4] = {0, 0, 0, 0};
+            if (r < a.rows0) {
+                if (a.xmode == 1) ldv<4>(va, a.hstore + ((blk * a.L + a.lx) * a.H + r) * M + m4);
+                else if (n > 0) {
+                    for (int q = 0; q < 4; ++q) va[q] = a.sigT[(blk - 1) * M + m4 + q] == r ? T(1) : T(0);
+                }
+            } else if (r < a.rows0 + a.rows1) {
+                if (!(a.hshift && n == 0)) ldv<4>(va, a.hstore + (((blk - a.hshift) * a.L + a.lh) * a.H + (r - a.rows0)) * M + m4);
+            } else if (r == R - 1) {
+                va[0] = va[1] = va[2] = va[3] = T(1);
+            }
+            if (cc < a.cols) ldv<4>(vb, a.B + (blk * a.cols + cc) * M + m4);
+            stv<4>(As + row * MS + m4, va);
+            stv<4>(Bs + row * MS + m4, vb);
+        }
+        __syncthreads();
+        T acc[4][4];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+        for (int m4 = 0; m4 < M; m4 += 4) {
+            T av[4][4], bv[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ldv<4>(av[i], As + (tr * 4 + i) * MS + m4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ldv<4>(bv[j], Bs + (tc * 4 + j) * MS + m4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[i][j] = fma(av[i][q], bv[j][q], acc[i][j]);
+        }
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) accd[i][j] += (double)acc[i][j];
+        __syncthreads();
+    }
+    const int Rp = a.rtiles * kWgTile, Cp = a.ctiles * kWgTile;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            partial[((size_t)ks * Rp + r0 + tr * 4 + i) * Cp + c0 + tc * 4 + j] = accd[i][j];
+}
+
+// sum the split-K partials (fixed order) and scatter into the flat gradient.
+//   layer mode : rows [x (d) | h (H) | ones], cols [da_r (H) | da_u (H) | da_c (H) | dq (H)]
+//   head mode  : rows [h_top (H) | ones],     cols [dz (2) | dz_phase (2)]
+__global__ void wgrad_scatter_kernel(const double* __restrict__ partial, int ksplit, int Rp, int Cp, GruLayout g, int l, int head,
+                                     double* __restrict__ grad) {
+    const int H = g.H;
+    const int d = head ? 0 : g.d[l];
+    const int R = d + H + 1, Ccols = head ? 2 * g.nheads : 4 * H;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < R * Ccols; idx += gridDim.x * blockDim.x) {
+        const int r = idx / Ccols, cidx = idx % Ccols;
+        int dst = -1;
+        if (head) {
+            const int hd = cidx / 2, o = cidx % 2;
+            const int base = g.flat_head + hd * (2 * H + 2);
+            dst = r < H ? base + r * 2 + o : base + 2 * H + o;
+        } else {
+            const int gate = cidx / H, j = cidx % H;
+            const int Kg = g.flat_off[l], bg = Kg + (d + H) * 2 * H, Kci = bg + 2 * H, Kch = Kci + d * H, bci = Kch + H * H,
+                      bch = bci + H;
+            if (r < d) {
+                if (gate < 2) dst = Kg + r * 2 * H + gate * H + j;
+                else if (gate == 2) dst = Kci + r * H + j;
+            } else if (r < d + H) {
+                const int k = r - d;
+                if (gate < 2) dst = Kg + (d + k) * 2 * H + gate * H + j;
+                else if (gate == 3) dst = Kch + k * H + j;
+            } else {
+                dst = gate < 2 ? bg + gate * H + j : gate == 2 ? bci + j : bch + j;
+            }
+        }
+        if (dst < 0) continue;
+        double s = 0.0;
+        for (int k = 0; k < ksplit; ++k) s += partial[((size_t)k * Rp + r) * Cp + cidx];
+        grad[dst] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+template <typename T> inline BwdLaunch choose_bwd_launch(const GruLayout& g) {
+    constexpr int SPT = VT<T>::SPT;
+    BwdLaunch best;
+    memset(&best, 0, sizeof(best));
+    const int per = align4(3 * g.H * g.CT * 2);
+    int maxpk = 0;
+    for (int l = 0; l < g.L; ++l) maxpk = std::max(maxpk, g.pk_size[l]);
+    const int dmax = g.L > 1 ? g.H : 0;
+    for (int wsm = 1; wsm >= 0; --wsm) {
+        double best_eff = -1.0;
+        for (int RT = 1; RT <= 64; ++RT) {
+            const int nt = g.CT * RT, M = RT * SPT;
+            if (nt > 384 || M > 2 * kHeadThreads) break;
+            const int Mp = (M + 15) & ~15;
+            size_t smem = (wsm ? (((size_t)(maxpk + 2 * per) * sizeof(T) + 15) & ~(size_t)15) : 0) +
+                          (size_t)(dmax + g.H + 4 * g.H + 4) * M * sizeof(T) + Mp + 64;
+            // the forward pass of the gradient runs with the same M: all layers' weights + L*H*M state
+            size_t fwd = (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) + (size_t)g.L * g.H * M * sizeof(T) + 2 * (size_t)Mp + 64;
+            if (smem > (size_t)kSmemLimit) break;
+            if (fwd > (size_t)kSmemLimit && wsm) break;
+            const double eff = (double)nt / (128.0 * (double)((nt + 127) / 128));
+            if (eff >= best_eff - 0.03) {
+                if (eff > best_eff) best_eff = eff;
+                best.CT = g.CT; best.RT = RT; best.M = M; best.Mp = Mp; best.NT = (nt + 31) & ~31;
+                best.w_smem = wsm; best.smem_bytes = (int)smem;
+            }
+        }
+        if (best.RT > 0) return best;
+    }
+    return best;
+}
+
+template <typename T> struct GradWs {
+    GruWs<T> f;
+    T* pkT;
+    double* roww;
+    T *dxbuf, *Gbuf, *dzbuf;
+    double* partial;
+    int ksplit, Rp, Cp;
+};
+
+template <typename T>
+static GradWs<T> carve_grad(Ws& ws, const GruLayout& g, const GruLayoutT& gt, const GruLaunch& cf, int64_t tiles, bool cplx,
+                            int64_t ns) {
+    GradWs<T> w;
+    w.f = carve_gru<T>(ws, g, cf, tiles, true, 0, cplx, ns);
+    const size_t rows = (size_t)tiles * cf.M;
+    w.pkT = ws.take<T>(gt.total);
+    w.roww = ws.take<double>(rows * (cplx ? 2 : 1));
+    w.dxbuf = ws.take<T>(g.L > 1 ? rows * g.N * g.H : 0);
+    w.Gbuf = ws.take<T>(rows * g.N * 4 * g.H);
+    w.dzbuf = ws.take<T>(rows * g.N * (cplx ? 4 : 2));
+    const int R = g.H + g.H + 1, C = 4 * g.H;
+    w.Rp = (int)cdiv(R, kWgTile) * kWgTile;
+    w.Cp = (int)cdiv(C, kWgTile) * kWgTile;
+    const int ntile = (w.Rp / kWgTile) * (w.Cp / kWgTile);
+    w.ksplit = (int)std::max<int64_t>(1, std::min<int64_t>((148 * 4 + ntile - 1) / ntile, tiles * g.N));
+    w.partial = ws.take<double>((size_t)w.ksplit * w.Rp * w.Cp);
+    return w;
+}
+
+template <typename T> static GruLaunch fwd_launch_for(const GruLayout& g, const BwdLaunch& b) {
+    GruLaunch c;
+    c.CT = b.CT; c.RT = b.RT; c.M = b.M; c.Mp = b.Mp; c.NTc = b.NT;
+    size_t with_w = (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) + (size_t)g.L * g.H * b.M * sizeof(T) + 2 * (size_t)b.Mp + 64;
+    c.w_smem = with_w <= (size_t)kSmemLimit;
+    c.smem_bytes = (int)(c.w_smem ? with_w : (size_t)g.L * g.H * b.M * sizeof(T) + 2 * (size_t)b.Mp + 64);
+    return c;
+}
+
+template <typename T> size_t gru_grad_workspace_bytes(const rnnwf_model& m, int64_t ns, int flags) {
+    const GruLayout g = make_gru_layout(m);
+    const GruLayoutT gt = make_gru_layout_T(g);
+    const BwdLaunch b = choose_bwd_launch<T>(g);
+    if (b.RT == 0) return 0;
+    const GruLaunch cf = fwd_launch_for<T>(g, b);
+    const int ndir = (flags & RNNWF_PARITY_SYM) ? 2 : 1;
+    Ws ws(nullptr, 0);
+    carve_grad<T>(ws, g, gt, cf, ndir * cdiv(ns, b.M), m.head == RNNWF_HEAD_COMPLEX, ns);
+    return ws.used + 256;
+}
+template size_t gru_grad_workspace_bytes<float>(const rnnwf_model&, int64_t, int);
+template size_t gru_grad_workspace_bytes<double>(const rnnwf_model&, int64_t, int);
+
+template <typename T, bool CPLX>
+static int launch_bwd_layer(const GruLayout& g, const GruLayoutT& gt, const BwdLaunch& b, int l, const GradWs<T>& w, int tiles,
+                            int64_t rows_total, cudaStream_t s) {
+    // per-layer smem: this layer's weights + transposed copies + tiles
+    if (b.w_smem) {
+        auto k = gru_bwd_layer_kernel<T, true, CPLX>;
+        if (int e = set_smem(k, b.smem_bytes)) return e;
+        k<<<tiles, b.NT, b.smem_bytes, s>>>(g, gt, b, l, w.f.pk, w.pkT, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.ph_sel, w.roww,
+                                            rows_total, w.dxbuf, w.Gbuf, w.dzbuf);
+    } else {
+        auto k = gru_bwd_layer_kernel<T, false, CPLX>;
+        if (int e = set_smem(k, b.smem_bytes)) return e;
+        k<<<tiles, b.NT, b.smem_bytes, s>>>(g, gt, b, l, w.f.pk, w.pkT, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.ph_sel, w.roww,
+                                            rows_total, w.dxbuf, w.Gbuf, w.dzbuf);
+    }
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int launch_wgrad(const GruLayout& g, const GradWs<T>& w, int M, int64_t nblk, int l, bool head, double* grad, cudaStream_t s) {
+    WgradArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.hstore = w.f.hstore; a.sigT = w.f.sigT; a.L = g.L; a.H = g.H; a.M = M; a.N = g.N; a.nblk = nblk;
+    if (head) {
+        a.B = w.dzbuf; a.xmode = 0; a.rows0 = 0; a.lh = g.L - 1; a.hshift = 0; a.rows1 = g.H; a.cols = 2 * g.nheads;
+    } else {
+        a.B = w.Gbuf; a.xmode = l > 0 ? 1 : 2; a.lx = l - 1; a.rows0 = g.d[l]; a.lh = l; a.hshift = 1; a.rows1 = g.H; a.cols = 4 * g.H;
+    }
+    const int R = a.rows0 + a.rows1 + 1;
+    a.rtiles = (int)cdiv(R, kWgTile);
+    a.ctiles = (int)cdiv(a.cols, kWgTile);
+    a.ksplit = w.ksplit;
+    const int smem = 2 * kWgTile * (M + 4) * (int)sizeof(T);
+    auto k = wgrad_kernel<T>;
+    if (int e = set_smem(k, smem)) return e;
+    k<<<dim3(a.rtiles * a.ctiles, a.ksplit), 256, smem, s>>>(a, w.partial);
+    RNNWF_CUDA(cudaGetLastError());
+    wgrad_scatter_kernel<<<grid_for((int64_t)R * a.cols), 256, 0, s>>>(w.partial, a.ksplit, a.rtiles * kWgTile, a.ctiles * kWgTile, g, l,
+                                                                    head ? 1 : 0, grad);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, const double* weights, int flags,
+                   double* grad, void* wsp, size_t wsb, cudaStream_t s) {
+    const GruLayout g = make_gru_layout(m);
+    const GruLayoutT gt = make_gru_layout_T(g);
+    const BwdLaunch b = choose_bwd_launch<T>(g);
+    RNNWF_CHECK(b.RT > 0, -3, "no backward launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
+    const GruLaunch cf = fwd_launch_for<T>(g, b);
+    const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
+    const int parity = (flags & RNNWF_PARITY_SYM) ? 1 : 0;
+    RNNWF_CHECK(!(cplx && parity), -2, "parity symmetry is only defined for the probability head");
+    const int tiles_s = (int)cdiv(ns, b.M), ndir = parity ? 2 : 1, tiles = tiles_s * ndir;
+    const int64_t rows_total = (int64_t)tiles * b.M;
+    Ws ws(wsp, wsb);
+    GradWs<T> w = carve_grad<T>(ws, g, gt, cf, tiles, cplx, ns);
+    RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
+    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.f.pk);
+    pack_gru_T_kernel<T><<<grid_for(gt.total), 256, 0, s>>>(g, gt, (const T*)params, w.pkT);
+    sig_transpose_kernel<<<grid_for(rows_total * g.N), 256, 0, s>>>(samples, w.f.sigT, ns, g.N, b.M, tiles_s, ndir);
+    int e = cplx ? launch_forward<T, true, true>(g, cf, w.f, tiles, s) : launch_forward<T, true, false>(g, cf, w.f, tiles, s);
+    if (e) return e;
+    row_weight_kernel<<<grid_for(rows_total), 256, 0, s>>>(weights, w.f.lp_re, ns, b.M, tiles_s, parity, cplx, w.roww);
+    for (int l = g.L - 1; l >= 0; --l) {
+        e = cplx ? launch_bwd_layer<T, true>(g, gt, b, l, w, tiles, rows_total, s) : launch_bwd_layer<T, false>(g, gt, b, l, w, tiles, rows_total, s);
+        if (e) return e;
+        if (l == g.L - 1)
+            if ((e = launch_wgrad<T>(g, w, b.M, (int64_t)tiles * g.N, l, true, grad, s))) return e;
+        if ((e = launch_wgrad<T>(g, w, b.M, (int64_t)tiles * g.N, l, false, grad, s))) return e;
+    }
+    return 0;
+}
+template int gru_vmc_grad_t<float>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, int, double*, void*, size_t,
+                                   cudaStream_t);
+template int gru_vmc_grad_t<double>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, int, double*, void*, size_t,
+                                    cudaStream_t);
+
+}  // namespace rnnwf

@@ -362,3 +362,5 @@ int tfim_enumerate_impl(const uint8_t* samples, int64_t ns, int N, int32_t* queu
 }
 
 }  // namespace rnnwf
+
+#include "grad.cuh"

@@ -127,18 +127,20 @@ __global__ void pack_gru_kernel(GruLayout g, const T* __restrict__ flat, T* __re
 // Ax == nullptr: the layer input is a one-hot / zero vector given by byte codes in `sig`
 // (0,1 = one-hot spin; 2 = the all-zero first input of RNNwavefunction.py:52-55).
 // ---------------------------------------------------------------------------------------------
+// Pre-activations of one layer on the thread's register tile:
+//   ar/au = gate pre-activations (incl. bias), ac = x Kci + bci, aq = h Kch + bch.
 template <typename T>
-__device__ __forceinline__ void gru_layer(const GruLayout& g, int l, const T* __restrict__ wl,
-                                          const T* __restrict__ Ax, const T* __restrict__ Ah,
-                                          const uint8_t* __restrict__ sig, int M, int ct, int rt,
-                                          T (&hn)[2][VT<T>::SPT]) {
+__device__ __forceinline__ void gru_preact(const GruLayout& g, int l, const T* __restrict__ wl,
+                                           const T* __restrict__ Ax, const T* __restrict__ Ah,
+                                           const uint8_t* __restrict__ sig, int M, int ct, int rt,
+                                           T (&ar)[2][VT<T>::SPT], T (&au)[2][VT<T>::SPT], T (&ac)[2][VT<T>::SPT],
+                                           T (&aq)[2][VT<T>::SPT]) {
     constexpr int SPT = VT<T>::SPT;
     const int H = g.H, CT = g.CT, d = g.d[l];
     const T* wx_ru = wl;
     const T* wx_c = wl + g.o_wx_c[l];
     const T* wh_ru = wl + g.o_wh_ru[l];
     const T* wh_c = wl + g.o_wh_c[l];
-    T ar[2][SPT], au[2][SPT], ac[2][SPT], aq[2][SPT];
     {
         T b[8];
         ldv<8>(b, wl + g.o_b[l] + ct * 8);
@@ -204,6 +206,18 @@ __device__ __forceinline__ void gru_layer(const GruLayout& g, int l, const T* __
             }
         }
     }
+}
+
+template <typename T>
+__device__ __forceinline__ void gru_layer(const GruLayout& g, int l, const T* __restrict__ wl,
+                                          const T* __restrict__ Ax, const T* __restrict__ Ah,
+                                          const uint8_t* __restrict__ sig, int M, int ct, int rt,
+                                          T (&hn)[2][VT<T>::SPT]) {
+    constexpr int SPT = VT<T>::SPT;
+    const int H = g.H;
+    T ar[2][SPT], au[2][SPT], ac[2][SPT], aq[2][SPT];
+    gru_preact<T>(g, l, wl, Ax, Ah, sig, M, ct, rt, ar, au, ac, aq);
+    const int row0 = rt * SPT;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int j = 2 * ct + u;

@@ -38,3 +38,7 @@ F = 75800.0
 steps = ns * N * (N + 1) / 2
 print(f"eloc    ns={ns}: {t:.1f} ms  mean E {e.mean().item():.3f}  -> {steps * F / t / 1e9:.2f} TFLOP/s algorithmic, "
       f"{ns / t * 1e3:.1f} samples/s")
+w = (e - e.mean()) / ns
+t, g = timed(lambda: ops.vmc_grad(model, flat, s, w))
+t, g = timed(lambda: ops.vmc_grad(model, flat, s, w))
+print(f"grad    ns={ns}: {t:.1f} ms  |g| {g.norm().item():.4e}")

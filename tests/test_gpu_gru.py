@@ -190,3 +190,28 @@ def test_adam_and_moments():
     e = torch.tensor(rng.normal(size=777), device=dev())
     st = ops.energy_moments(e).cpu().numpy()
     np.testing.assert_allclose(st, [e.sum().item(), (e * e).sum().item(), 777], rtol=1e-12)
+
+
+@pytest.mark.parametrize("units,N,ns,parity", [([50], 20, 100, False), ([6, 6, 6], 11, 170, False), ([7, 7], 10, 90, True)])
+def test_vmc_gradient_matches_autograd(units, N, ns, parity):
+    from oracle import torch_grad as TG
+    p, model, flat = gru_setup(units, N, scale=2.0)
+    s = O.sample(p, ns, N, seed=5)
+    rng = np.random.default_rng(3)
+    e = rng.normal(size=ns)
+    w = (e - e.mean()) / ns
+    p64 = {k: v.astype(np.float64) for k, v in p.items()}
+    ref = TG.gru_vmc_grad(p64, s, w, parity=parity)
+    got = ops.vmc_grad(model, flat, u8(s), torch.tensor(w, device=dev()), flags=ops.PARITY_SYM if parity else 0).cpu().numpy()
+    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    assert err < 1e-4, err
+
+
+def test_vmc_gradient_f64_exact():
+    from oracle import torch_grad as TG
+    p, model, flat = gru_setup([5, 5], 9, dtype=np.float64, nx=3, ny=3)
+    s = O.sample(p, 40, 9, seed=2)
+    w = np.random.default_rng(0).normal(size=40)
+    ref = TG.gru_vmc_grad(p, s, w)
+    got = ops.vmc_grad(model, flat, u8(s), torch.tensor(w, device=dev())).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12)

@@ -151,3 +151,33 @@ def test_adam_tf1_first_step():
     th, m, v, t = O.adam_tf1(np.array([1.0]), np.array([0.5]), np.zeros(1), np.zeros(1), 0, 1e-2)
     # first step: lr_t*m/(sqrt(v)+eps) = lr*sqrt(1-b2)/(1-b1) * 0.05/(sqrt(0.00025)+1e-8)
     assert abs(th[0] - (1 - 1e-2 * math.sqrt(0.001) / 0.1 * 0.05 / (math.sqrt(0.00025) + 1e-8))) < 1e-15
+
+
+def test_autograd_oracle_matches_numpy_forward():
+    torch = pytest.importorskip("torch")
+    from oracle import torch_grad as TG
+    p = O.randomize_biases(O.init_gru_params([5, 5], seed=4, dtype=np.float64, scale=2.0))
+    s = np.random.default_rng(0).integers(0, 2, size=(7, 9))
+    lp = TG.gru_logprob_t(TG._t(p), [5, 5], s).detach().numpy()
+    np.testing.assert_allclose(lp, O.log_probability(p, s), rtol=1e-12)
+    pc = O.randomize_biases(O.init_gru_params([6], seed=9, dtype=np.float64, heads=("wf_dense_ampl", "wf_dense_phase"), scale=2.0))
+    sc = O.crnn_sample(pc, 9, 8, seed=3)
+    re, im = TG.crnn_logamp_t(TG._t(pc), [6], sc)
+    la = O.crnn_log_amplitude(pc, sc)
+    np.testing.assert_allclose(re.detach().numpy(), la.real, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(im.detach().numpy(), la.imag, rtol=1e-10, atol=1e-12)
+    pm = O.init_mdrnn_params(5, seed=2, dtype=np.float64, scale=2.0)
+    sm = np.random.default_rng(1).integers(0, 2, size=(6, 3, 4))
+    np.testing.assert_allclose(TG.mdrnn_logprob_t(TG._t(pm), sm).detach().numpy(), O.mdrnn_log_probability(pm, sm), rtol=1e-12)
+    # finite-difference check of the autograd gradient on one parameter
+    w = np.random.default_rng(2).normal(size=7)
+    g = TG.gru_vmc_grad(p, s, w)
+    flat = O.flatten(p)
+    shapes = O.gru_param_shapes([5, 5])
+    i = 37
+    e = 1e-6
+    fp, fm = flat.copy(), flat.copy()
+    fp[i] += e
+    fm[i] -= e
+    fd = ((w * O.log_probability(O.unflatten(fp, shapes), s)).sum() - (w * O.log_probability(O.unflatten(fm, shapes), s)).sum()) / (2 * e)
+    assert abs(fd - g[i]) < 1e-6 * max(1, abs(fd))
