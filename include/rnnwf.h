@@ -131,6 +131,19 @@ int rnnwf_adam_step(int dtype, int64_t n, void* theta, void* mom, void* vel, con
 /* Mean / population variance of E_loc: stats_out = {sum, sum of squares, count} (double[3]).             */
 int rnnwf_energy_moments(const double* eloc, int64_t ns, int stride, double* stats_out, void* stream);
 
+/* ---- measurement hooks (bench.py) --------------------------------------------------------------------------
+ * Between rnnwf_profile_begin() and rnnwf_profile_end() the library counts its kernel launches and brackets
+ * the dominant kernel of each call (the prefix-reuse chain kernel of rnnwf_tfim_eloc / rnnwf_j1j2_eloc) with
+ * CUDA events on the caller's stream.  rnnwf_profile_end() waits for those events and returns the launch count,
+ * the number of dominant-kernel launches and their summed device time.  Results of the compute entry points
+ * are unaffected.  (The reference has only commented-out time.time() prints, 1DTFIM/TrainingRNN_1DTFIM.py:53-54.) */
+int rnnwf_profile_begin(void);
+int rnnwf_profile_end(int64_t* launches_out, int64_t* dominant_launches_out, double* dominant_ms_out);
+
+/* FP32 FFMA throughput of the device (TFLOP/s) measured with a register-resident FMA kernel on `stream`:
+ * the denominator of the compute roofline the recurrence kernels are held against.        */
+int rnnwf_ffma_peak(int iters, double* tflops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

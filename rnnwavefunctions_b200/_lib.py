@@ -45,6 +45,9 @@ _SIGNATURES = {
     "rnnwf_adam_step": (C.c_int, [C.c_int, C.c_int64, _P, _P, _P, _P, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int64, _P]),
     "rnnwf_energy_moments": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P]),
+    "rnnwf_profile_begin": (C.c_int, []),
+    "rnnwf_profile_end": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "rnnwf_ffma_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -44,6 +44,7 @@ template <typename T> int mdrnn_vmc_grad_t(const rnnwf_model& m, const void* par
 // misc.cu
 int adam_step_impl(int dtype, int64_t n, void* theta, void* mom, void* vel, const double* grad, double grad_scale, double lr,
                    double b1, double b2, double eps, int64_t t, cudaStream_t s);
+int ffma_peak_impl(int iters, double* tflops, cudaStream_t s);
 int energy_moments_impl(const double* eloc, int64_t ns, int stride, double* stats, cudaStream_t s);
 
 }  // namespace rnnwf

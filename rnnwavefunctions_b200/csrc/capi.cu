@@ -10,6 +10,30 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+// measurement state (host only; one process per GPU, see include/rnnwf.h)
+static constexpr int kProfPairs = 256;
+static struct {
+    bool on = false;
+    long launches = 0;
+    int pairs = 0;
+    bool open = false;
+    cudaEvent_t ev[kProfPairs][2] = {};
+} g_prof;
+void prof_count(int n) { if (g_prof.on) g_prof.launches += n; }
+void prof_mark(int which, cudaStream_t s) {
+    if (!g_prof.on) return;
+    if (which == 0) {
+        if (g_prof.pairs >= kProfPairs) { g_prof.open = false; return; }
+        for (int k = 0; k < 2; ++k)
+            if (!g_prof.ev[g_prof.pairs][k]) cudaEventCreate(&g_prof.ev[g_prof.pairs][k]);
+        cudaEventRecord(g_prof.ev[g_prof.pairs][0], s);
+        g_prof.open = true;
+    } else if (g_prof.open) {
+        cudaEventRecord(g_prof.ev[g_prof.pairs][1], s);
+        g_prof.pairs++;
+        g_prof.open = false;
+    }
+}
 static int check_model(const rnnwf_model* m) {
     RNNWF_CHECK(m != nullptr, -1, "model is NULL");
     RNNWF_CHECK(m->cell == RNNWF_CELL_GRU || m->cell == RNNWF_CELL_MDRNN, -1, "unknown cell %d", m->cell);
@@ -37,6 +61,29 @@ extern "C" {
 
 RNNWF_API const char* rnnwf_last_error(void) { return g_err; }
 RNNWF_API int rnnwf_abi_version(void) { return RNNWF_ABI_VERSION; }
+
+RNNWF_API int rnnwf_profile_begin(void) {
+    g_prof.on = true;
+    g_prof.launches = 0;
+    g_prof.pairs = 0;
+    g_prof.open = false;
+    return 0;
+}
+
+RNNWF_API int rnnwf_profile_end(int64_t* launches_out, int64_t* dominant_launches_out, double* dominant_ms_out) {
+    g_prof.on = false;
+    double ms = 0.0;
+    for (int i = 0; i < g_prof.pairs; ++i) {
+        RNNWF_CUDA(cudaEventSynchronize(g_prof.ev[i][1]));
+        float t = 0.f;
+        RNNWF_CUDA(cudaEventElapsedTime(&t, g_prof.ev[i][0], g_prof.ev[i][1]));
+        ms += t;
+    }
+    if (launches_out) *launches_out = g_prof.launches;
+    if (dominant_launches_out) *dominant_launches_out = g_prof.pairs;
+    if (dominant_ms_out) *dominant_ms_out = ms;
+    return 0;
+}
 
 RNNWF_API int64_t rnnwf_param_count(const rnnwf_model* m) {
     if (check_model(m)) return -1;
@@ -130,6 +177,11 @@ RNNWF_API int rnnwf_adam_step(int dtype, int64_t n, void* theta, void* mom, void
 RNNWF_API int rnnwf_energy_moments(const double* eloc, int64_t ns, int stride, double* stats_out, void* stream) {
     RNNWF_CHECK(eloc && stats_out && ns > 0 && stride >= 1, -1, "bad arguments to rnnwf_energy_moments");
     return energy_moments_impl(eloc, ns, stride, stats_out, (cudaStream_t)stream);
+}
+
+RNNWF_API int rnnwf_ffma_peak(int iters, double* tflops_out, void* stream) {
+    RNNWF_CHECK(iters > 0 && tflops_out, -1, "bad arguments to rnnwf_ffma_peak");
+    return ffma_peak_impl(iters, tflops_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -31,6 +31,13 @@ void set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------
+// measurement hooks (capi.cu): launch counter + CUDA-event brackets around the dominant kernel.
+// Inactive unless rnnwf_profile_begin() was called; never changes what is computed.
+// ------------------------------------------------------------------------------------------------
+void prof_count(int n = 1);
+void prof_mark(int which, cudaStream_t s);   // which: 0 = before, 1 = after the dominant kernel of the call
+
 constexpr int kMaxLayers = 8;
 constexpr int kSmemLimit = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
 constexpr int kHeadThreads = 128;   // 4 "head" warps: dense + softmax + draw, overlapped with layer 0

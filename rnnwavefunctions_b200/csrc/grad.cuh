@@ -503,12 +503,12 @@ static int launch_bwd_layer(const GruLayout& g, const GruLayoutT& gt, const BwdL
     if (b.w_smem) {
         auto k = gru_bwd_layer_kernel<T, true, CPLX>;
         if (int e = set_smem(k, b.smem_bytes)) return e;
-        k<<<tiles, b.NT, b.smem_bytes, s>>>(g, gt, b, l, w.f.pk, w.pkT, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.ph_sel, w.roww,
+        prof_count(); k<<<tiles, b.NT, b.smem_bytes, s>>>(g, gt, b, l, w.f.pk, w.pkT, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.ph_sel, w.roww,
                                             rows_total, w.dxbuf, w.Gbuf, w.dzbuf);
     } else {
         auto k = gru_bwd_layer_kernel<T, false, CPLX>;
         if (int e = set_smem(k, b.smem_bytes)) return e;
-        k<<<tiles, b.NT, b.smem_bytes, s>>>(g, gt, b, l, w.f.pk, w.pkT, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.ph_sel, w.roww,
+        prof_count(); k<<<tiles, b.NT, b.smem_bytes, s>>>(g, gt, b, l, w.f.pk, w.pkT, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.ph_sel, w.roww,
                                             rows_total, w.dxbuf, w.Gbuf, w.dzbuf);
     }
     RNNWF_CUDA(cudaGetLastError());
@@ -532,9 +532,9 @@ static int launch_wgrad(const GruLayout& g, const GradWs<T>& w, int M, int64_t n
     const int smem = 2 * kWgTile * (M + 4) * (int)sizeof(T);
     auto k = wgrad_kernel<T>;
     if (int e = set_smem(k, smem)) return e;
-    k<<<dim3(a.rtiles * a.ctiles, a.ksplit), 256, smem, s>>>(a, w.partial);
+    prof_count(); k<<<dim3(a.rtiles * a.ctiles, a.ksplit), 256, smem, s>>>(a, w.partial);
     RNNWF_CUDA(cudaGetLastError());
-    wgrad_scatter_kernel<<<grid_for((int64_t)R * a.cols), 256, 0, s>>>(w.partial, a.ksplit, a.rtiles * kWgTile, a.ctiles * kWgTile, g, l,
+    prof_count(); wgrad_scatter_kernel<<<grid_for((int64_t)R * a.cols), 256, 0, s>>>(w.partial, a.ksplit, a.rtiles * kWgTile, a.ctiles * kWgTile, g, l,
                                                                     head ? 1 : 0, grad);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
@@ -556,12 +556,12 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
     Ws ws(wsp, wsb);
     GradWs<T> w = carve_grad<T>(ws, g, gt, cf, tiles, cplx, ns);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
-    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.f.pk);
-    pack_gru_T_kernel<T><<<grid_for(gt.total), 256, 0, s>>>(g, gt, (const T*)params, w.pkT);
-    sig_transpose_kernel<<<grid_for(rows_total * g.N), 256, 0, s>>>(samples, w.f.sigT, ns, g.N, b.M, tiles_s, ndir);
+    prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.f.pk);
+    prof_count(); pack_gru_T_kernel<T><<<grid_for(gt.total), 256, 0, s>>>(g, gt, (const T*)params, w.pkT);
+    prof_count(); sig_transpose_kernel<<<grid_for(rows_total * g.N), 256, 0, s>>>(samples, w.f.sigT, ns, g.N, b.M, tiles_s, ndir);
     int e = cplx ? launch_forward<T, true, true>(g, cf, w.f, tiles, s) : launch_forward<T, true, false>(g, cf, w.f, tiles, s);
     if (e) return e;
-    row_weight_kernel<<<grid_for(rows_total), 256, 0, s>>>(weights, w.f.lp_re, ns, b.M, tiles_s, parity, cplx, w.roww);
+    prof_count(); row_weight_kernel<<<grid_for(rows_total), 256, 0, s>>>(weights, w.f.lp_re, ns, b.M, tiles_s, parity, cplx, w.roww);
     for (int l = g.L - 1; l >= 0; --l) {
         e = cplx ? launch_bwd_layer<T, true>(g, gt, b, l, w, tiles, rows_total, s) : launch_bwd_layer<T, false>(g, gt, b, l, w, tiles, rows_total, s);
         if (e) return e;

@@ -197,11 +197,11 @@ static int launch_forward(const GruLayout& g, const GruLaunch& c, const GruWs<T>
     if (c.w_smem) {
         auto k = gru_forward_kernel<T, true, STASH, CPLX>;
         if (int e = set_smem(k, c.smem_bytes)) return e;
-        k<<<tiles, block, c.smem_bytes, s>>>(g, c, w.pk, w.sigT, w.lp_re, w.lp_im, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth);
+        prof_count(); k<<<tiles, block, c.smem_bytes, s>>>(g, c, w.pk, w.sigT, w.lp_re, w.lp_im, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth);
     } else {
         auto k = gru_forward_kernel<T, false, STASH, CPLX>;
         if (int e = set_smem(k, c.smem_bytes)) return e;
-        k<<<tiles, block, c.smem_bytes, s>>>(g, c, w.pk, w.sigT, w.lp_re, w.lp_im, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth);
+        prof_count(); k<<<tiles, block, c.smem_bytes, s>>>(g, c, w.pk, w.sigT, w.lp_re, w.lp_im, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth);
     }
     RNNWF_CUDA(cudaGetLastError());
     return 0;
@@ -215,18 +215,20 @@ static int launch_chain(const GruLayout& g, const GruLaunch& c, const ChainPlan&
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)std::min<int64_t>((int64_t)plan.nslots * plan.tiles, sms);
     RNNWF_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), s));
-    chain_order_kernel<<<1, 1, 0, s>>>(plan, w.order);
+    prof_count(); chain_order_kernel<<<1, 1, 0, s>>>(plan, w.order);
+    prof_mark(0, s);
     if (c.w_smem) {
         auto k = gru_chain_kernel<T, true, CPLX>;
         if (int e = set_smem(k, c.smem_bytes)) return e;
-        k<<<grid, block, c.smem_bytes, s>>>(g, c, plan, w.pk, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth, w.order,
+        prof_count(); k<<<grid, block, c.smem_bytes, s>>>(g, c, plan, w.pk, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth, w.order,
                                             w.delta_re, w.delta_im, w.counter);
     } else {
         auto k = gru_chain_kernel<T, false, CPLX>;
         if (int e = set_smem(k, c.smem_bytes)) return e;
-        k<<<grid, block, c.smem_bytes, s>>>(g, c, plan, w.pk, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth, w.order,
+        prof_count(); k<<<grid, block, c.smem_bytes, s>>>(g, c, plan, w.pk, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth, w.order,
                                             w.delta_re, w.delta_im, w.counter);
     }
+    prof_mark(1, s);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }
@@ -238,11 +240,11 @@ static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, ui
     if (c.w_smem) {
         auto k = gru_sample_kernel<T, true, CPLX>;
         if (int e = set_smem(k, c.smem_bytes)) return e;
-        k<<<tiles, block, c.smem_bytes, s>>>(g, c, pk, sampT, seed, off);
+        prof_count(); k<<<tiles, block, c.smem_bytes, s>>>(g, c, pk, sampT, seed, off);
     } else {
         auto k = gru_sample_kernel<T, false, CPLX>;
         if (int e = set_smem(k, c.smem_bytes)) return e;
-        k<<<tiles, block, c.smem_bytes, s>>>(g, c, pk, sampT, seed, off);
+        prof_count(); k<<<tiles, block, c.smem_bytes, s>>>(g, c, pk, sampT, seed, off);
     }
     RNNWF_CUDA(cudaGetLastError());
     return 0;
@@ -283,11 +285,11 @@ int gru_sample_t(const rnnwf_model& m, const void* params, int64_t ns, uint64_t 
     Ws ws(wsp, wsb);
     GruWs<T> w = carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
-    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
+    prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
     int e = cplx ? launch_sample<T, true>(g, c, w.pk, w.sigT, tiles, seed, off, s)
                  : launch_sample<T, false>(g, c, w.pk, w.sigT, tiles, seed, off, s);
     if (e) return e;
-    samp_untranspose_kernel<<<grid_for(ns * g.N), 256, 0, s>>>(w.sigT, out, ns, g.N, c.M);
+    prof_count(); samp_untranspose_kernel<<<grid_for(ns * g.N), 256, 0, s>>>(w.sigT, out, ns, g.N, c.M);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }
@@ -307,11 +309,11 @@ int gru_logpsi_t(const rnnwf_model& m, const void* params, const uint8_t* sample
     Ws ws(wsp, wsb);
     GruWs<T> w = carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
-    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
-    sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
+    prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
+    prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
     int e = cplx ? launch_forward<T, false, true>(g, c, w, tiles, s) : launch_forward<T, false, false>(g, c, w, tiles, s);
     if (e) return e;
-    gather_logpsi_kernel<<<grid_for(ns), 256, 0, s>>>(w.lp_re, w.lp_im, ns, c.M, tiles_s, parity, cplx, out);
+    prof_count(); gather_logpsi_kernel<<<grid_for(ns), 256, 0, s>>>(w.lp_re, w.lp_im, ns, c.M, tiles_s, parity, cplx, out);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }
@@ -330,9 +332,9 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     Ws ws(wsp, wsb);
     GruWs<T> w = carve_gru<T>(ws, g, c, tiles, true, g.N, false, ns);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
-    pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
-    sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
-    tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
+    prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
+    prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
+    prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
     if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
         if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
         ChainPlan plan{g.N, g.N, 0, 0, tiles};
@@ -340,7 +342,7 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     } else {
         if (int e = launch_forward<T, false, false>(g, c, w, tiles, s)) return e;
     }
-    tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(w.diag, w.delta_re, w.lp_re, ns, g.N, c.M, tiles_s, bx, parity, eloc, logp);
+    prof_count(); tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(w.diag, w.delta_re, w.lp_re, ns, g.N, c.M, tiles_s, bx, parity, eloc, logp);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }
@@ -350,13 +352,13 @@ template int gru_tfim_eloc_t<double>(const rnnwf_model&, const void*, const uint
                                      double*, void*, size_t, cudaStream_t);
 
 int tfim_diag_impl(const rnnwf_model& m, const uint8_t* samples, int64_t ns, const double* jz, double* diag, cudaStream_t s) {
-    tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, m.n_sites, m.nx, m.ny, jz, diag);
+    prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, m.n_sites, m.nx, m.ny, jz, diag);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }
 
 int tfim_enumerate_impl(const uint8_t* samples, int64_t ns, int N, int32_t* queue, cudaStream_t s) {
-    tfim_enumerate_kernel<<<grid_for((int64_t)(N + 1) * ns * N), 256, 0, s>>>(samples, ns, N, queue);
+    prof_count(); tfim_enumerate_kernel<<<grid_for((int64_t)(N + 1) * ns * N), 256, 0, s>>>(samples, ns, N, queue);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }

@@ -22,6 +22,7 @@ int adam_step_impl(int dtype, int64_t n, void* theta, void* mom, void* vel, cons
                    double b2, double eps, int64_t t, cudaStream_t s) {
     const double lr_t = lr * sqrt(1.0 - pow(b2, (double)t)) / (1.0 - pow(b1, (double)t));
     const int grid = (int)std::min<int64_t>(cdiv(n, 256), 1184);
+    prof_count();
     if (dtype == RNNWF_F32)
         adam_kernel<float><<<grid, 256, 0, s>>>(n, (float*)theta, (float*)mom, (float*)vel, grad, gs, lr_t, b1, b2, eps);
     else
@@ -57,8 +58,51 @@ __global__ void moments_kernel(const double* __restrict__ e, int64_t ns, int str
 }
 
 int energy_moments_impl(const double* eloc, int64_t ns, int stride, double* stats, cudaStream_t s) {
+    prof_count();
     moments_kernel<<<1, 256, 0, s>>>(eloc, ns, stride, stats);
     RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// FFMA peak probe: 16 independent accumulator chains per thread, 2 FMAs per chain per iteration.
+__global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float a, float b, float* __restrict__ out) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456f) out[0] = s;
+}
+
+int ffma_peak_impl(int iters, double* tflops, cudaStream_t s) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    float* out = nullptr;
+    RNNWF_CUDA(cudaMalloc(&out, 4));
+    cudaEvent_t e0, e1;
+    RNNWF_CUDA(cudaEventCreate(&e0));
+    RNNWF_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 8;
+    ffma_probe_kernel<<<grid, 256, 0, s>>>(iters / 8 + 1, 0.999f, 0.001f, out);
+    RNNWF_CUDA(cudaEventRecord(e0, s));
+    ffma_probe_kernel<<<grid, 256, 0, s>>>(iters, 0.999f, 0.001f, out);
+    RNNWF_CUDA(cudaEventRecord(e1, s));
+    RNNWF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RNNWF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *tflops = 2.0 * 64.0 * (double)iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
     return 0;
 }
 

@@ -177,8 +177,28 @@ def adam_step(model, theta, mom, vel, grad, t, lr, grad_scale=1.0, beta1=0.9, be
                                       float(lr), beta1, beta2, eps, int(t), _stream()))
 
 
-def energy_moments(eloc_f64, stride=1):
-    ns = eloc_f64.numel() // stride
+def energy_moments(eloc_f64, stride=1, count=None):
+    """-> float64 [3] = (sum, sum of squares, n) over eloc_f64[0], eloc_f64[stride], ... (count entries)."""
+    ns = eloc_f64.numel() // stride if count is None else int(count)
     out = torch.empty(3, dtype=torch.float64, device=eloc_f64.device)
     check(_lib.load().rnnwf_energy_moments(_ptr(eloc_f64), ns, stride, _ptr(out), _stream()))
     return out
+
+
+def profile_begin():
+    """Start counting this library's kernel launches and timing the dominant (chain) kernel."""
+    check(_lib.load().rnnwf_profile_begin())
+
+
+def profile_end():
+    """-> (kernel launches, dominant-kernel launches, dominant-kernel device ms) since profile_begin()."""
+    a, b, c = C.c_int64(0), C.c_int64(0), C.c_double(0.0)
+    check(_lib.load().rnnwf_profile_end(C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def ffma_peak(iters=20000):
+    """Measured FP32 FFMA throughput of the current device in TFLOP/s."""
+    out = C.c_double(0.0)
+    check(_lib.load().rnnwf_ffma_peak(int(iters), C.byref(out), _stream()))
+    return out.value

@@ -1,0 +1,78 @@
+"""CPU-side checks of the drop-in boundary: librnnwf_b200.so builds for sm_100a, loads without a GPU and
+exports every symbol include/rnnwf.h declares; argument validation happens before any CUDA call."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from rnnwavefunctions_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build(verbose=False)
+    return _lib.load()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rnnwf.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rnnwf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rnnwf.h but not exported"
+        assert n in _lib.EXPORTS, f"{n} has no ctypes signature in _lib.py"
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_abi_version_and_param_counts(lib):
+    assert lib.rnnwf_abi_version() == 1
+    # parameter counts pinned by the reference notebooks: 422 (Tutorial_1DTFIM.ipynb#cell15), 444 (Tutorial_1DJ1J2.ipynb#cell15)
+    m = _lib.Model(_lib.CELL_GRU, _lib.HEAD_PROB, _lib.F32, 1, 10, 10, 0, 0)
+    assert lib.rnnwf_param_count(C.byref(m)) == 422
+    m = _lib.Model(_lib.CELL_GRU, _lib.HEAD_COMPLEX, _lib.F32, 1, 10, 10, 0, 0)
+    assert lib.rnnwf_param_count(C.byref(m)) == 444
+    m = _lib.Model(_lib.CELL_GRU, _lib.HEAD_PROB, _lib.F32, 3, 50, 1000, 0, 0)
+    assert lib.rnnwf_param_count(C.byref(m)) == 38502          # cfg2
+    m = _lib.Model(_lib.CELL_MDRNN, _lib.HEAD_PROB, _lib.F64, 1, 100, 144, 12, 12)
+    assert lib.rnnwf_param_count(C.byref(m)) == 20702          # cfg4
+
+
+def test_errors_are_reported_not_raised(lib):
+    bad = _lib.Model(7, 0, 0, 1, 10, 10, 0, 0)
+    assert lib.rnnwf_param_count(C.byref(bad)) == -1
+    assert b"unknown cell" in lib.rnnwf_last_error()
+    odd = _lib.Model(_lib.CELL_GRU, _lib.HEAD_COMPLEX, _lib.F32, 1, 10, 11, 0, 0)
+    assert lib.rnnwf_param_count(C.byref(odd)) == -1           # zero magnetisation needs even N
+    m = _lib.Model(_lib.CELL_GRU, _lib.HEAD_PROB, _lib.F32, 1, 10, 10, 0, 0)
+    rc = lib.rnnwf_sample(C.byref(m), None, 10, 0, 0, None, None, 0, None)
+    assert rc == -1 and b"bad arguments" in lib.rnnwf_last_error()
+    with pytest.raises(_lib.RnnwfError):
+        _lib.check(rc)
+
+
+def test_workspace_sizes_scale_with_samples(lib):
+    m = _lib.Model(_lib.CELL_GRU, _lib.HEAD_PROB, _lib.F32, 3, 50, 1000, 0, 0)
+    a = lib.rnnwf_workspace_bytes(C.byref(m), _lib.OP_TFIM_ELOC, 1200, 0)
+    b = lib.rnnwf_workspace_bytes(C.byref(m), _lib.OP_TFIM_ELOC, 2400, 0)
+    assert 0 < a < b < 2.2 * a
+    # hidden-state stash: N*L*H*4 B = 600 KB per sample
+    assert a / 1200 > 600e3
+    par = lib.rnnwf_workspace_bytes(C.byref(m), _lib.OP_TFIM_ELOC, 1200, _lib.PARITY_SYM)
+    assert 1.9 * a < par < 2.1 * a
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rnnwavefunctions_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
