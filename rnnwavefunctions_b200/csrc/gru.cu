@@ -337,7 +337,7 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
     if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
         if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
-        ChainPlan plan{g.N, g.N, 0, 0, tiles};
+        ChainPlan plan{g.N, g.N, 0, 0, tiles, nullptr, nullptr};
         if (int e = launch_chain<T, false>(g, c, plan, w, s)) return e;
     } else {
         if (int e = launch_forward<T, false, false>(g, c, w, tiles, s)) return e;
@@ -366,3 +366,4 @@ int tfim_enumerate_impl(const uint8_t* samples, int64_t ns, int N, int32_t* queu
 }  // namespace rnnwf
 
 #include "grad.cuh"
+#include "j1j2.cuh"

@@ -214,6 +214,8 @@ struct ChainPlan {
     int n_kind1;      // next n_kind1 slots: kind 1 with s = slot - n_kind0
     int n_kind2;      // next n_kind2 slots: kind 2
     int tiles;        // sample tiles (all directions)
+    const double* j1; // optional couplings: a kind-1 (kind-2) slot with j1[s] == 0 (j2[s] == 0) is skipped,
+    const double* j2; //   as the reference's `J[site] != 0.0` guards do (J1J2/TrainingRNN_J1J2.py:69,84)
 };
 
 __device__ __forceinline__ void chain_decode(const ChainPlan& p, int slot, int& kind, int& s) {
@@ -251,6 +253,10 @@ gru_chain_kernel(GruLayout g, GruLaunch c, ChainPlan plan, const T* __restrict__
         int kind, s;
         chain_decode(plan, slot, kind, s);
         const int t = kind == 0 ? -1 : s + kind;           // second modified site (exchange partner)
+        if ((kind == 1 && plan.j1 && plan.j1[s] == 0.0) || (kind == 2 && plan.j2 && plan.j2[s] == 0.0)) {
+            __syncthreads();   // s_work is rewritten at the top of the loop
+            continue;
+        }
         const uint8_t* sigtile = sigT + (size_t)st * N * M;
         {   // restart state: every layer's h after site s of the base pass
             const T* src = hstore + ((size_t)st * N + s) * L * H * M;

@@ -2,10 +2,6 @@
 #include "api_internal.h"
 namespace rnnwf {
 #define NOTIMPL(name) do { set_error(name " is not implemented in this build"); return -2; } while (0)
-int j1j2_enumerate_impl(const uint8_t*, int64_t, int, const double*, const double*, const double*, int, int, int32_t*, float*, int32_t*, cudaStream_t) { NOTIMPL("j1j2_enumerate"); }
-template <typename T> int gru_j1j2_eloc_t(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, const double*, const double*, int, double*, double*, void*, size_t, cudaStream_t) { NOTIMPL("j1j2_eloc"); }
-template int gru_j1j2_eloc_t<float>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, const double*, const double*, int, double*, double*, void*, size_t, cudaStream_t);
-template int gru_j1j2_eloc_t<double>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, const double*, const double*, int, double*, double*, void*, size_t, cudaStream_t);
 template <typename T> size_t mdrnn_workspace_bytes_t(const rnnwf_model&, int, int64_t, int) { return 0; }
 template size_t mdrnn_workspace_bytes_t<float>(const rnnwf_model&, int, int64_t, int);
 template size_t mdrnn_workspace_bytes_t<double>(const rnnwf_model&, int, int64_t, int);
