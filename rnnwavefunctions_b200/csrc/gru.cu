@@ -357,6 +357,13 @@ int tfim_diag_impl(const rnnwf_model& m, const uint8_t* samples, int64_t ns, con
     return 0;
 }
 
+int tfim_finalize_impl(const double* diag, const double* delta, const double* lp, int64_t ns, int N, int M, int tiles_s, double bx,
+                       int parity, double* eloc, double* logp, cudaStream_t s) {
+    prof_count(); tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(diag, delta, lp, ns, N, M, tiles_s, bx, parity, eloc, logp);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int tfim_enumerate_impl(const uint8_t* samples, int64_t ns, int N, int32_t* queue, cudaStream_t s) {
     prof_count(); tfim_enumerate_kernel<<<grid_for((int64_t)(N + 1) * ns * N), 256, 0, s>>>(samples, ns, N, queue);
     RNNWF_CUDA(cudaGetLastError());
