@@ -432,6 +432,7 @@ template <typename T> inline BwdLaunch choose_bwd_launch(const GruLayout& g) {
             size_t fwd = (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) + (size_t)g.L * g.H * M * sizeof(T) + 2 * (size_t)Mp + 64;
             if (smem > (size_t)kSmemLimit) break;
             if (fwd > (size_t)kSmemLimit && wsm) break;
+            if ((size_t)2 * 64 * (M + 4) * sizeof(T) > (size_t)kSmemLimit) break;   // wgrad_kernel staging tiles (kWgTile = 64)
             const double eff = (double)nt / (128.0 * (double)((nt + 127) / 128));
             if (eff >= best_eff - 0.03) {
                 if (eff > best_eff) best_eff = eff;
