@@ -23,6 +23,10 @@ import sys
 import tempfile
 import time
 
+if "reference" in sys.argv:      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -64,6 +68,11 @@ class CpuReference:
         from oracle import rnnwf_oracle as O
         from oracle import torch_grad as TG
         self.O, self.TG = O, TG
+        try:
+            import torch
+            torch.set_num_threads(os.cpu_count() or 1)
+        except Exception:
+            pass
         self.N, self.parity = n_sites, parity
         self.units = [UNITS] * LAYERS
         self.p = O.init_gru_params(self.units, seed=111, dtype=np.float32)

@@ -43,6 +43,9 @@ template <typename T> int mdrnn_tfim_eloc_t(const rnnwf_model& m, const void* pa
 template <typename T> int mdrnn_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns,
                                            const double* weights, double* grad, void* ws, size_t wsb, cudaStream_t s);
 
+// umma_selftest.cu
+int umma_selftest_impl(int N, int K, const float* A, const float* B, float* D, int passes, cudaStream_t s);
+
 // misc.cu
 int adam_step_impl(int dtype, int64_t n, void* theta, void* mom, void* vel, const double* grad, double grad_scale, double lr,
                    double b1, double b2, double eps, int64_t t, cudaStream_t s);

@@ -184,4 +184,9 @@ RNNWF_API int rnnwf_ffma_peak(int iters, double* tflops_out, void* stream) {
     return ffma_peak_impl(iters, tflops_out, (cudaStream_t)stream);
 }
 
+RNNWF_API int rnnwf_umma_selftest(int n, int k, const float* a, const float* b, float* d, int passes, void* stream) {
+    RNNWF_CHECK(a && b && d, -1, "bad arguments to rnnwf_umma_selftest");
+    return umma_selftest_impl(n, k, a, b, d, passes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -202,3 +202,11 @@ def ffma_peak(iters=20000):
     out = C.c_double(0.0)
     check(_lib.load().rnnwf_ffma_peak(int(iters), C.byref(out), _stream()))
     return out.value
+
+
+def umma_selftest(a, b, passes=3):
+    """d = a @ b.T on the tcgen05 path (a [128,K], b [N,K] float32 CUDA tensors)."""
+    n, k = b.shape
+    d = torch.empty((128, n), dtype=torch.float32, device=a.device)
+    check(_lib.load().rnnwf_umma_selftest(n, k, _ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(d), passes, _stream()))
+    return d
