@@ -1,5 +1,7 @@
 // gru.cu — host launchers + utility kernels for the GRU wave functions (1-D pRNN, parity-symmetric pRNN,
 // 1-D RNN over a flattened 2-D lattice, complex cRNN) and the TFIM / J1-J2 local energies built on them.
+#include <stdlib.h>
+#include <type_traits>
 #include "gru_kernels.cuh"
 #include "host_util.cuh"
 #include "api_internal.h"
@@ -250,6 +252,17 @@ static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, ui
     return 0;
 }
 
+}  // namespace rnnwf
+#include "gru_tc.cuh"
+namespace rnnwf {
+
+// RNNWF_CHAIN=ffma forces the CUDA-core chain kernel (A/B measurements); default: tensor cores where supported
+static bool use_tc_chain(const GruLayout& g) {
+    const char* e = getenv("RNNWF_CHAIN");
+    if (e && strcmp(e, "ffma") == 0) return false;
+    return tc_supported(g);
+}
+
 // ---------------------------------------------------------------------------------------------
 // typed implementations behind the C ABI
 // ---------------------------------------------------------------------------------------------
@@ -264,7 +277,10 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
     switch (op) {
         case RNNWF_OP_SAMPLE:
         case RNNWF_OP_LOGPSI: carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns); break;
-        case RNNWF_OP_TFIM_ELOC: carve_gru<T>(ws, g, c, tiles, true, g.N, cplx, ns); break;
+        case RNNWF_OP_TFIM_ELOC:
+            carve_gru<T>(ws, g, c, tiles, true, g.N, cplx, ns);
+            if (std::is_same<T, float>::value && tc_supported(g)) carve_tc(ws, g, make_tc_layout(g), 160);
+            break;
         case RNNWF_OP_J1J2_ELOC: carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns); ws.take<float>((size_t)ns * (2 * g.N + 1)); break;
         case RNNWF_OP_VMC_GRAD: return gru_grad_workspace_bytes<T>(m, ns, flags);
         default: return 0;
@@ -331,11 +347,18 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     const int tiles_s = (int)cdiv(ns, c.M), ndir = parity ? 2 : 1, tiles = tiles_s * ndir;
     Ws ws(wsp, wsb);
     GruWs<T> w = carve_gru<T>(ws, g, c, tiles, true, g.N, false, ns);
+    TcWs tw{};
+    const bool tc = std::is_same<T, float>::value && tc_supported(g);
+    if (tc) tw = carve_tc(ws, g, make_tc_layout(g), 160);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
     prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
     prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
-    if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
+    if (tc && use_tc_chain(g)) {
+        if constexpr (std::is_same<T, float>::value) {
+            if (int e = launch_eloc_tc(g, c, w, tw, tiles, (const float*)params, bx != 0.0, s)) return e;
+        }
+    } else if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
         if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
         ChainPlan plan{g.N, g.N, 0, 0, tiles, nullptr, nullptr};
         if (int e = launch_chain<T, false>(g, c, plan, w, s)) return e;

@@ -122,6 +122,30 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                  : "memory");
 }
 
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v[0])) : "memory");
+}
+// store CNT (<= 8) consecutive columns starting at an 8-aligned column: 8 | 4 + 2 + 1 pieces, each size-aligned
+template <int CNT> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float (&v)[8]) {
+    if constexpr (CNT >= 8) {
+        tmem_st8(taddr, v);
+    } else {
+        int o = 0;
+        if constexpr ((CNT & 4) != 0) { tmem_st4(taddr + o, v + o); o += 4; }
+        if constexpr ((CNT & 2) != 0) { tmem_st2(taddr + o, v + o); o += 2; }
+        if constexpr ((CNT & 1) != 0) { tmem_st1(taddr + o, v + o); }
+    }
+}
+
 // fp32 -> (hi, lo) with hi exactly representable in TF32 (round to nearest) and lo = x - hi rounded to TF32:
 // hi*w_hi + lo*w_hi + hi*w_lo reproduces the FP32 product to ~2^-21 relative (3xTF32).
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
@@ -132,6 +156,14 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     uint32_t l;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
     lo = __uint_as_float(l);
+}
+
+// same, leaving lo unrounded: kind::tf32 reads only sign, exponent and the upper 10 mantissa bits of its operands
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
 }
 
 }  // namespace umma

@@ -1,6 +1,6 @@
 """Quick device timing of the cfg2 stages (not the bench contract; used while developing)."""
+import os
 import sys
-import time
 
 import numpy as np
 import torch
@@ -30,14 +30,18 @@ def timed(fn, reps=1):
 t, s = timed(lambda: ops.sample(model, flat, ns, seed=1))
 t, s = timed(lambda: ops.sample(model, flat, ns, seed=1))
 print(f"sample  ns={ns}: {t:.1f} ms  mean spin {s.float().mean().item():.3f}")
-t, lp = timed(lambda: ops.logpsi(model, flat, s))
-t, lp = timed(lambda: ops.logpsi(model, flat, s))
-print(f"logpsi  ns={ns}: {t:.1f} ms  mean lp {lp.mean().item():.3f}")
-t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
 F = 75800.0
 steps = ns * N * (N + 1) / 2
-print(f"eloc    ns={ns}: {t:.1f} ms  mean E {e.mean().item():.3f}  -> {steps * F / t / 1e9:.2f} TFLOP/s algorithmic, "
-      f"{ns / t * 1e3:.1f} samples/s")
+res = {}
+for chain in ("ffma", "tc"):
+    os.environ["RNNWF_CHAIN"] = chain
+    t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
+    t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
+    res[chain] = e
+    print(f"eloc[{chain:4s}] ns={ns}: {t:.1f} ms  mean E {e.mean().item():.4f}  -> {steps * F / t / 1e9:.2f} TFLOP/s algorithmic, "
+          f"{ns / t * 1e3:.1f} samples/s")
+d = (res["tc"] - res["ffma"]).abs() / res["ffma"].abs()
+print(f"tc vs ffma: max rel diff {d.max().item():.2e}")
 w = (e - e.mean()) / ns
 t, g = timed(lambda: ops.vmc_grad(model, flat, s, w))
 t, g = timed(lambda: ops.vmc_grad(model, flat, s, w))
