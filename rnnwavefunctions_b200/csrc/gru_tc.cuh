@@ -26,7 +26,7 @@ namespace rnnwf {
 
 constexpr int kTcRows = 128;      // rows per tile = UMMA M = TMEM lanes
 constexpr int kTcBlk = 64;        // column block per gate in D / row block per gate in B
-constexpr int kTcT = 8;           // sites per layer block (inter-layer scratch = T * 128 * 52 * 4 B per CTA, kept small to stay in L2)
+constexpr int kTcT = 16;           // sites per layer block (inter-layer scratch = T * 128 * 52 * 4 B per CTA, kept small to stay in L2)
 constexpr int kTcThreads = 288;   // 8 row warps + 1 MMA warp
 
 struct TcLayout {
@@ -149,6 +149,13 @@ __device__ __forceinline__ void tc_stage_group(uint32_t lane_addr, uint32_t colH
     }
 }
 template <int H, int PART>
+__device__ __forceinline__ void tc_stage_g(int gq, uint32_t lane_addr, uint32_t colHi, uint32_t colLo, const float* v) {
+    if (gq == 0) tc_stage_group<H, PART, 0>(lane_addr, colHi, colLo, v);
+    else if (gq == 1) tc_stage_group<H, PART, 1>(lane_addr, colHi, colLo, v);
+    else if (gq == 2) tc_stage_group<H, PART, 2>(lane_addr, colHi, colLo, v);
+    else tc_stage_group<H, PART, 3>(lane_addr, colHi, colLo, v);
+}
+template <int H, int PART>
 __device__ __forceinline__ void tc_stage(uint32_t lane_addr, uint32_t colHi, uint32_t colLo, const float* v) {
     tc_stage_group<H, PART, 0>(lane_addr, colHi, colLo, v);
     tc_stage_group<H, PART, 1>(lane_addr, colHi, colLo, v);
@@ -185,6 +192,7 @@ struct TcArgs {
     float *xbuf, *hsave;
     double* delta;          // FLIP: [tile][slot][M]
     int* counter;
+    long long* dbg;         // optional [grid][4] cycle counters: {mma wait, gate math, staging/barrier, steps} of row thread 0
 };
 
 // all row-thread work of one (block, layer): restore the state, then nb sites of {stage operands, wait for the MMAs, gate math}
@@ -231,17 +239,21 @@ __device__ __forceinline__ void tc_row_block(const TcArgs& a, const float* tab, 
     } else {
         tc_load_row<H, PART>(xb + ((size_t)0 * kTcRows + rowi) * HP, xr);
     }
+    long long tq3 = a.dbg ? clock64() : 0;
     for (int tt = 0; tt < nb; ++tt) {
         const int n = b0 + tt;
         if (l > 0) {
-            tc_stage<H, PART>(lane_addr, colXH, colXL, xr);
+            if (tt == 0) tc_stage<H, PART>(lane_addr, colXH, colXL, xr);   // later sites: staged during the previous site's gate math
         } else if (PART == 0) {
             const float oh[8] = {code == 0 ? 1.f : 0.f, code == 1 ? 1.f : 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             umma::tmem_st8(lane_addr + colXH, oh);
         }
+        const long long tq4 = a.dbg ? clock64() : 0;
         umma::wait_st();
+        const long long tq5 = a.dbg ? clock64() : 0;
         umma::fence_before_sync();
         tc_named_sync();
+        const long long tq0 = a.dbg ? clock64() : 0;
         // ---- the MMA warp issues this site's MMAs now; fetch what the next steps need meanwhile ----
         int sg = 0;
         double lsel = 0.0;
@@ -256,6 +268,7 @@ __device__ __forceinline__ void tc_row_block(const TcArgs& a, const float* tab, 
         umma::mbar_wait(&bars[0], par_mma);
         par_mma ^= 1;
         umma::fence_after_sync();
+        const long long tq1 = a.dbg ? clock64() : 0;
         // ---- gate math.  D holds a_r = -log2e * pre_r, a_u likewise, a_cx, a_ch = 2 log2e * (candidate parts), biases included ----
         float z0 = 0.f, z1 = 0.f;
 #pragma unroll
@@ -286,25 +299,41 @@ __device__ __forceinline__ void tc_row_block(const TcArgs& a, const float* tab, 
                     if (BASE && live) a.hstore[(((rowbase + n) * L + l) * (size_t)H + j) * Mold + m] = h;
                 }
             }
+            // operands of the next MMAs for this group of units (the MMAs of this site are complete: both regions are free),
+            // interleaved with the MUFU-bound gate math of the following group
+            tc_stage_g<H, PART>(gq, lane_addr, colHH, colHL, hp);
+            if (l > 0 && tt + 1 < nb) tc_stage_g<H, PART>(gq, lane_addr, colXH, colXL, xr);
+            if (!top) {
+                float4* dst = reinterpret_cast<float4*>(xb + ((size_t)tt * kTcRows + rowi) * HP + P::U0 + 8 * gq);
+                dst[0] = make_float4(hp[8 * gq], hp[8 * gq + 1], hp[8 * gq + 2], hp[8 * gq + 3]);
+                if (cnt > 4) dst[1] = make_float4(hp[8 * gq + 4], hp[8 * gq + 5], hp[8 * gq + 6], hp[8 * gq + 7]);
+            }
         }
-        tc_stage<H, PART>(lane_addr, colHH, colHL, hp);                                 // H operand of the next site
-        if (!top) tc_store_row<H, PART>(xb + ((size_t)tt * kTcRows + rowi) * HP, hp);     // input of the next layer
+        const long long tq2 = a.dbg ? clock64() : 0;
         if (top) {
             if (PART == 1) zsm[rowi] = make_float2(z0, z1);
             tc_row_sync();
             if (PART == 0 && live) {
                 const float2 o = zsm[rowi];
                 const float f0 = z0 + o.x + tab[2 * kTcBlk], f1 = z1 + o.y + tab[2 * kTcBlk + 1];
-                const double zs = sg ? (double)f1 : (double)f0, zo = sg ? (double)f0 : (double)f1;
-                const double ls = log_softmax2(zs, zo);
+                // log softmax of the 2-way head in FP32 (log1pf/expf, ~1e-7 relative); the site terms are summed in FP64
+                const float dsel = sg ? f0 - f1 : f1 - f0;                         // z_other - z_selected
+                const double ls = dsel > 30.f ? -(double)dsel : -(double)log1pf(expf(dsel));
+                const double lo_ = -dsel > 30.f ? (double)dsel : -(double)log1pf(expf(-dsel));
                 if (BASE) {
                     a.la_sel[(rowbase + n) * Mold + m] = ls;
-                    a.la_oth[(rowbase + n) * Mold + m] = log_softmax2(zo, zs);
+                    a.la_oth[(rowbase + n) * Mold + m] = lo_;
                     acc += ls;
                 } else {
                     acc += ls - lsel;
                 }
             }
+        }
+        if (a.dbg && rowi == 0) {
+            long long* d = a.dbg + 16 * blockIdx.x + 8 * PART;
+            d[4] += tq4 - tq3; d[5] += tq5 - tq4; d[6] += tq0 - tq5;
+            tq3 = clock64();
+            d[0] += tq1 - tq0; d[1] += tq2 - tq1; d[2] += tq3 - tq2; d[3] += 1;
         }
     }
     if (b0 + nb < N) tc_store_row<H, PART>(hs + ((size_t)l * kTcRows + rowi) * HP, hp);   // park h^l for the next block
@@ -447,6 +476,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) gru_chain_tc_kernel(const __gri
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 8) umma::tmem_dealloc(tbase, 512);
+    if (a.dbg && (tid == 0 || tid == 128) && blockIdx.x < 1) {
+        const long long* d = a.dbg + 16 * blockIdx.x + 8 * (tid >> 7);
+        const double n = (double)d[3];
+        printf("[tc dbg] base=%d part %d: steps %lld | x-stage %.0f wait_st %.0f named-sync %.0f | mma-wait %.0f gate-math %.0f h-stage+head %.0f cycles/step\n",
+               (int)BASE, tid >> 7, d[3], d[4] / n, d[5] / n, d[6] / n, d[0] / n, d[1] / n, d[2] / n);
+    }
 }
 
 struct TcWs {
@@ -465,7 +500,7 @@ inline TcWs carve_tc(Ws& ws, const GruLayout& g, const TcLayout& t, int sms) {
     w.img = ws.take<float>((size_t)g.L * t.img_floats);
     w.tab = ws.take<float>(t.tab_floats);
     w.xbuf = ws.take<float>((size_t)sms * kTcT * kTcRows * HP);
-    w.hsave = ws.take<float>((size_t)sms * g.L * kTcRows * HP);
+    w.hsave = ws.take<float>((size_t)sms * g.L * kTcRows * HP + 4096);   // + room for the optional debug counters
     return w;
 }
 
@@ -482,11 +517,13 @@ static int launch_eloc_tc(const GruLayout& g, const GruLaunch& c, const GruWs<fl
     a.tiles128 = (int)cdiv(a.rows_total, kTcRows);
     a.img = tw.img; a.tabg = tw.tab; a.sigT = w.sigT; a.hstore = w.hstore; a.la_sel = w.la_sel; a.la_oth = w.la_oth; a.lp = w.lp_re;
     a.xbuf = tw.xbuf; a.hsave = tw.hsave; a.delta = w.delta_re; a.counter = w.counter;
+    a.dbg = getenv("RNNWF_TC_DEBUG") ? reinterpret_cast<long long*>(tw.hsave + (size_t)sms * g.L * kTcRows * (((g.H + 3) / 4) * 4)) : nullptr;
     const int smem = (int)tc_smem_bytes(t);
     RNNWF_CHECK(smem <= kSmemLimit, -3, "tensor-core chain kernel needs %d bytes of shared memory", smem);
     prof_count(); pack_gru_tc_kernel<<<grid_for(g.L * (t.s1 + t.s2 + t.sx)), 256, 0, s>>>(g, t, params, tw.img, tw.tab);
     {
         RNNWF_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), s));
+        if (a.dbg) RNNWF_CUDA(cudaMemsetAsync(a.dbg, 0, 4096 * sizeof(float), s));
         auto k = gru_chain_tc_kernel<50, true>;
         if (int e = set_smem(k, smem)) return e;
         prof_count();
@@ -495,6 +532,7 @@ static int launch_eloc_tc(const GruLayout& g, const GruLaunch& c, const GruWs<fl
     }
     if (flips) {
         RNNWF_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), s));
+        if (a.dbg) RNNWF_CUDA(cudaMemsetAsync(a.dbg, 0, 4096 * sizeof(float), s));
         auto k = gru_chain_tc_kernel<50, false>;
         if (int e = set_smem(k, smem)) return e;
         const int grid = (int)std::min<int64_t>((int64_t)g.N * a.tiles128, sms);

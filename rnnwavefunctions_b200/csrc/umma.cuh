@@ -160,9 +160,7 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 // same, leaving lo unrounded: kind::tf32 reads only sign, exponent and the upper 10 mantissa bits of its operands
 __device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);   // round half away in magnitude; finite inputs only
     lo = x - hi;
 }
 
