@@ -145,7 +145,8 @@ int rnnwf_profile_end(int64_t* launches_out, int64_t* dominant_launches_out, dou
 int rnnwf_ffma_peak(int iters, double* tflops_out, void* stream);
 
 /* Known-answer check of the tcgen05 / TMEM plumbing the tensor-core recurrence kernels are built on:
- * d[128][n] = a[128][k] * b[n][k]^T on one CTA (A staged in TMEM, B in shared memory, `passes` = 1: TF32, 3: 3xTF32). */
+ * d[128][n] = a[128][k] * b[n][k]^T on one CTA (A staged in TMEM, B in shared memory, `passes` = 1: TF32, 3: 3xTF32;
+ * passes = -(p + 4*dcol): the FP16 path with p in {1, 3} passes and the accumulator at TMEM column dcol). */
 int rnnwf_umma_selftest(int n, int k, const float* a, const float* b, float* d, int passes, void* stream);
 
 #ifdef __cplusplus

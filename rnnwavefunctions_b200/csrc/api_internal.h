@@ -44,6 +44,7 @@ template <typename T> int mdrnn_vmc_grad_t(const rnnwf_model& m, const void* par
                                            const double* weights, double* grad, void* ws, size_t wsb, cudaStream_t s);
 
 // umma_selftest.cu
+int umma_selftest_f16_impl(int N, int K, const float* A, const float* B, float* D, int passes, int dcol, cudaStream_t s);
 int umma_selftest_impl(int N, int K, const float* A, const float* B, float* D, int passes, cudaStream_t s);
 
 // misc.cu

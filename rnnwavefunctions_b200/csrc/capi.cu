@@ -186,6 +186,7 @@ RNNWF_API int rnnwf_ffma_peak(int iters, double* tflops_out, void* stream) {
 
 RNNWF_API int rnnwf_umma_selftest(int n, int k, const float* a, const float* b, float* d, int passes, void* stream) {
     RNNWF_CHECK(a && b && d, -1, "bad arguments to rnnwf_umma_selftest");
+    if (passes < 0) return umma_selftest_f16_impl(n, k, a, b, d, (-passes) & 3, (-passes) >> 2, (cudaStream_t)stream);
     return umma_selftest_impl(n, k, a, b, d, passes, (cudaStream_t)stream);
 }
 

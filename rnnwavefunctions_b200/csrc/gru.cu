@@ -254,13 +254,18 @@ static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, ui
 
 }  // namespace rnnwf
 #include "gru_tc.cuh"
+#include "gru_tc16.cuh"
 namespace rnnwf {
 
-// RNNWF_CHAIN=ffma forces the CUDA-core chain kernel (A/B measurements); default: tensor cores where supported
-static bool use_tc_chain(const GruLayout& g) {
+// Chain-kernel selection for the FP32 probability-head pRNN (A/B measurements through RNNWF_CHAIN):
+//   default / "tc16": tcgen05 kind::f16, 3xFP16 operands, all weights resident (gru_tc16.cuh)
+//   "tc32"          : tcgen05 kind::tf32, 3xTF32 operands, site-blocked weight swapping (gru_tc.cuh)
+//   "ffma"          : CUDA-core tile engine (gru_chain_kernel; the path every other shape / dtype takes)
+static int chain_mode(const GruLayout& g) {
     const char* e = getenv("RNNWF_CHAIN");
-    if (e && strcmp(e, "ffma") == 0) return false;
-    return tc_supported(g);
+    if (e && strcmp(e, "ffma") == 0) return 0;
+    if (e && strcmp(e, "tc32") == 0) return tc_supported(g) ? 1 : 0;
+    return tc16::supported(g) ? 2 : (tc_supported(g) ? 1 : 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -280,6 +285,7 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
         case RNNWF_OP_TFIM_ELOC:
             carve_gru<T>(ws, g, c, tiles, true, g.N, cplx, ns);
             if (std::is_same<T, float>::value && tc_supported(g)) carve_tc(ws, g, make_tc_layout(g), 160);
+            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
             break;
         case RNNWF_OP_J1J2_ELOC: carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns); ws.take<float>((size_t)ns * (2 * g.N + 1)); break;
         case RNNWF_OP_VMC_GRAD: return gru_grad_workspace_bytes<T>(m, ns, flags);
@@ -350,11 +356,20 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     TcWs tw{};
     const bool tc = std::is_same<T, float>::value && tc_supported(g);
     if (tc) tw = carve_tc(ws, g, make_tc_layout(g), 160);
+    unsigned char* img16 = nullptr;
+    if (std::is_same<T, float>::value && tc16::supported(g)) img16 = ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
+    const int mode = std::is_same<T, float>::value ? chain_mode(g) : 0;
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
     prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
     prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
-    if (tc && use_tc_chain(g)) {
+    if (mode == 2) {
+        if constexpr (std::is_same<T, float>::value) {
+            if (int e = tc16::launch_eloc(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.lp_re, w.delta_re,
+                                          w.counter, bx != 0.0, s))
+                return e;
+        }
+    } else if (mode == 1) {
         if constexpr (std::is_same<T, float>::value) {
             if (int e = launch_eloc_tc(g, c, w, tw, tiles, (const float*)params, bx != 0.0, s)) return e;
         }

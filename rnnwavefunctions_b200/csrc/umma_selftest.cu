@@ -2,6 +2,7 @@
 // TMEM addressing): D[128 x N] = A[128 x K] * B[N x K]^T with A staged in TMEM and B in shared memory, 1xTF32 or 3xTF32.
 // Test infrastructure for the tensor-core recurrence kernels; exposed through rnnwf_umma_selftest.
 #include "api_internal.h"
+#include <cuda_fp16.h>
 #include "umma.cuh"
 
 namespace rnnwf {
@@ -90,6 +91,109 @@ umma_selftest_kernel(int N, int K, const float* __restrict__ A, const float* __r
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 4) umma::tmem_dealloc(tbase, 512);
+}
+
+// ---- same check for the FP16 path: kind::f16, A = fp16 pairs packed in TMEM columns (k even in the low half),
+// B = fp16 K-major core matrices (8 rows x 8 halfs), 3 passes hi*hi + lo*hi + hi*lo; D is read back at column offset
+// `dcol` (any value: checks that tcgen05.ld/st need no column alignment).
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half = a, high half = b
+    return r;
+}
+__device__ __forceinline__ float h_lo_of(float x) {   // x - fp16(x)
+    const __half h = __float2half_rn(x);
+    return x - __half2float(h);
+}
+
+__global__ void __launch_bounds__(160, 1)
+umma_selftest_f16_kernel(int N, int K, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int passes, int dcol) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Kp = (K + 15) & ~15, KC = Kp / 8;
+    const uint32_t b_bytes = (uint32_t)N * Kp * 2;
+    __half* Bhi = reinterpret_cast<__half*>(smem);
+    __half* Blo = reinterpret_cast<__half*>(smem + b_bytes);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * b_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 2 * b_bytes + 8);
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    if (warp == 4) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        umma::mbar_init(bar, 1);
+        umma::mbar_fence_init();
+    }
+    for (int i = tid; i < N * Kp; i += blockDim.x) {
+        const int n = i / Kp, k = i % Kp;
+        const float v = k < K ? B[n * K + k] : 0.f;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const int off = (n / 8) * (KC * 64) + (k / 8) * 64 + (n % 8) * 8 + (k % 8);   // in halfs
+        Bhi[off] = hi;
+        Blo[off] = lo;
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t colD = (uint32_t)dcol, colAhi = 300, colAlo = 300 + 36;     // deliberately unaligned bases
+    if (warp < 4) {
+        const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+        for (int c = 0; c < Kp / 2; ++c) {
+            const int k = 2 * c;
+            const float a0 = k < K ? A[tid * K + k] : 0.f, a1 = k + 1 < K ? A[tid * K + k + 1] : 0.f;
+            const float h0 = __half2float(__float2half_rn(a0)), h1 = __half2float(__float2half_rn(a1));
+            float hi[1] = {__uint_as_float(pack_h2(a0, a1))}, lo[1] = {__uint_as_float(pack_h2(a0 - h0, a1 - h1))};
+            umma::tmem_st1(lane_addr + colAhi + c, hi);
+            umma::tmem_st1(lane_addr + colAlo + c, lo);
+        }
+        umma::wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4 && lane == 0) {
+        umma::fence_after_sync();
+        const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F16 x F16 -> F32
+        const uint32_t bhi = umma::smem_u32(Bhi), blo = umma::smem_u32(Blo);
+        uint32_t acc = 0;
+        for (int pass = 0; pass < passes; ++pass) {
+            const uint32_t acol = pass == 1 ? colAlo : colAhi;
+            const uint32_t bsm = pass == 2 ? blo : bhi;
+            for (int ks = 0; ks < Kp / 16; ++ks) {
+                const uint64_t bd = umma::smem_desc(bsm + ks * 256, 128, KC * 128);
+                umma::mma_f16_ts(tbase + colD, tbase + acol + ks * 8, bd, idesc, acc);
+                acc = 1;
+            }
+        }
+        umma::commit(bar);
+    }
+    if (warp < 4) {
+        umma::mbar_wait(bar, 0);
+        umma::fence_after_sync();
+        const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+        for (int n0 = 0; n0 < N; n0 += 8) {
+            float v[8];
+            umma::tmem_ld8(lane_addr + colD + n0, v);
+            umma::wait_ld();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (n0 + q < N) D[tid * N + n0 + q] = v[q];
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) umma::tmem_dealloc(tbase, 512);
+}
+
+int umma_selftest_f16_impl(int N, int K, const float* A, const float* B, float* D, int passes, int dcol, cudaStream_t s) {
+    RNNWF_CHECK(N >= 16 && N <= 256 && N % 16 == 0 && K >= 1 && K <= 64 && (passes == 1 || passes == 3) && dcol >= 0 && dcol + N <= 300, -1,
+                "umma f16 selftest: bad shape");
+    const int Kp = (K + 15) & ~15;
+    const int smem = 2 * N * Kp * 2 + 64;
+    RNNWF_CUDA(cudaFuncSetAttribute(umma_selftest_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    prof_count();
+    umma_selftest_f16_kernel<<<1, 160, smem, s>>>(N, K, A, B, D, passes, dcol);
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int umma_selftest_impl(int N, int K, const float* A, const float* B, float* D, int passes, cudaStream_t s) {

@@ -204,9 +204,11 @@ def ffma_peak(iters=20000):
     return out.value
 
 
-def umma_selftest(a, b, passes=3):
-    """d = a @ b.T on the tcgen05 path (a [128,K], b [N,K] float32 CUDA tensors)."""
+def umma_selftest(a, b, passes=3, f16=False, dcol=0):
+    """d = a @ b.T on the tcgen05 path (a [128,K], b [N,K] float32 CUDA tensors); f16: FP16 hi/lo operands."""
     n, k = b.shape
+    if f16:
+        passes = -(passes + 4 * dcol)
     d = torch.empty((128, n), dtype=torch.float32, device=a.device)
     check(_lib.load().rnnwf_umma_selftest(n, k, _ptr(a.contiguous()), _ptr(b.contiguous()), _ptr(d), passes, _stream()))
     return d

@@ -33,15 +33,16 @@ print(f"sample  ns={ns}: {t:.1f} ms  mean spin {s.float().mean().item():.3f}")
 F = 75800.0
 steps = ns * N * (N + 1) / 2
 res = {}
-for chain in ("ffma", "tc"):
+for chain in ("ffma", "tc32", "tc16"):
     os.environ["RNNWF_CHAIN"] = chain
     t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
     t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
     res[chain] = e
-    print(f"eloc[{chain:4s}] ns={ns}: {t:.1f} ms  mean E {e.mean().item():.4f}  -> {steps * F / t / 1e9:.2f} TFLOP/s algorithmic, "
+    print(f"eloc[{chain:5s}] ns={ns}: {t:.1f} ms  mean E {e.mean().item():.4f}  -> {steps * F / t / 1e9:.2f} TFLOP/s algorithmic, "
           f"{ns / t * 1e3:.1f} samples/s")
-d = (res["tc"] - res["ffma"]).abs() / res["ffma"].abs()
-print(f"tc vs ffma: max rel diff {d.max().item():.2e}")
+for c in ("tc32", "tc16"):
+    d = (res[c] - res["ffma"]).abs() / res["ffma"].abs()
+    print(f"{c} vs ffma: max rel diff {d.max().item():.2e}")
 w = (e - e.mean()) / ns
 t, g = timed(lambda: ops.vmc_grad(model, flat, s, w))
 t, g = timed(lambda: ops.vmc_grad(model, flat, s, w))

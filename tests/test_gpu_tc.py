@@ -33,8 +33,9 @@ def eloc_with(chain, model, flat, s, Jz, Bx, flags=0):
             os.environ["RNNWF_CHAIN"] = old
 
 
+@pytest.mark.parametrize("chain", ["tc16", "tc32"])
 @pytest.mark.parametrize("L,N,ns,parity", [(1, 20, 150, False), (3, 37, 300, False), (2, 24, 70, True), (3, 130, 260, False)])
-def test_tc_chain_matches_ffma_and_oracle(L, N, ns, parity):
+def test_tc_chain_matches_ffma_and_oracle(L, N, ns, parity, chain):
     units = [50] * L
     p = O.randomize_biases(O.init_gru_params(units, seed=L, dtype=np.float32, scale=2.0), seed=L + 1)
     model = ops.make_model(num_layers=L, units=50, n_sites=N)
@@ -42,7 +43,7 @@ def test_tc_chain_matches_ffma_and_oracle(L, N, ns, parity):
     s = O.sample(p, ns, N, seed=3)
     Jz = np.random.default_rng(5).uniform(0.5, 1.5, size=N)
     flags = ops.PARITY_SYM if parity else 0
-    e_tc, lp_tc = eloc_with("tc", model, flat, u8(s), Jz, 0.9, flags)
+    e_tc, lp_tc = eloc_with(chain, model, flat, u8(s), Jz, 0.9, flags)
     e_ff, lp_ff = eloc_with("ffma", model, flat, u8(s), Jz, 0.9, flags)
     np.testing.assert_allclose(e_tc, e_ff, rtol=2e-5)      # two FP32-grade evaluations; each is held to 1e-5 against the oracle below
     np.testing.assert_allclose(lp_tc, lp_ff, rtol=1e-5)
