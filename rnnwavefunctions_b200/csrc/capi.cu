@@ -130,6 +130,11 @@ RNNWF_API int rnnwf_tfim_eloc(const rnnwf_model* m, const void* params, const ui
     return DISPATCH(m, gru_tfim_eloc_t, *m, params, samples, ns, jz, bx, flags, eloc_out, logp_out, ws, ws_bytes, s);
 }
 
+RNNWF_API int rnnwf_tfim_chain_mode(const rnnwf_model* m) {
+    if (check_model(m)) return -1;
+    return tfim_chain_mode_impl(*m);
+}
+
 RNNWF_API int rnnwf_tfim_diag(const rnnwf_model* m, const uint8_t* samples, int64_t ns, const double* jz, double* diag_out, void* stream) {
     if (int e = check_model(m)) return e;
     RNNWF_CHECK(samples && jz && diag_out && ns > 0, -1, "bad arguments to rnnwf_tfim_diag");

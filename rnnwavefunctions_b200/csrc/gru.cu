@@ -389,6 +389,11 @@ template int gru_tfim_eloc_t<float>(const rnnwf_model&, const void*, const uint8
 template int gru_tfim_eloc_t<double>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, double, int, double*,
                                      double*, void*, size_t, cudaStream_t);
 
+int tfim_chain_mode_impl(const rnnwf_model& m) {
+    if (m.cell != RNNWF_CELL_GRU || m.dtype != RNNWF_F32 || m.head != RNNWF_HEAD_PROB) return 0;
+    return chain_mode(make_gru_layout(m));
+}
+
 int tfim_diag_impl(const rnnwf_model& m, const uint8_t* samples, int64_t ns, const double* jz, double* diag, cudaStream_t s) {
     prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, m.n_sites, m.nx, m.ny, jz, diag);
     RNNWF_CUDA(cudaGetLastError());

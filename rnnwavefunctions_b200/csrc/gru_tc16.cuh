@@ -211,22 +211,34 @@ __device__ __forceinline__ void row_step(const Args& a, const float* tab, float2
         umma::tmem_ld8(col + 2 * kBW, du);
         umma::tmem_ld8(col + 3 * kBW, dq);
         umma::wait_ld();
+        // gates of two units at a time: 1/(1+2^a) for r0, u0, r1, u1 share ONE reciprocal (exponents clamped to 30, so the
+        // product of the four denominators stays below 2^121), and so do the two candidates' 1/(1+2^c)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 0; q < 8; q += 2) {
             if (q < cnt) {
                 const int jl = 8 * gq + q, j = P::U0 + jl;
-                const float er = 1.0f + ex2(fminf(dr[q], 60.f)), eu = 1.0f + ex2(fminf(du[q], 60.f));
-                const float inv = rcp(er * eu);                          // one reciprocal for both gates
-                const float r = inv * eu, u = inv * er;
-                const float ec = 1.0f + ex2(fmaf(r, dq[q], dc[q]));
-                const float cc = fmaf(-2.0f, rcp(ec), 1.0f);
-                const float h = fmaf(u, hp[jl] - cc, cc);
-                hp[jl] = h;
+                const float er0 = 1.0f + ex2(fminf(dr[q], 30.f)), eu0 = 1.0f + ex2(fminf(du[q], 30.f));
+                const float er1 = 1.0f + ex2(fminf(dr[q + 1], 30.f)), eu1 = 1.0f + ex2(fminf(du[q + 1], 30.f));
+                const float p0 = er0 * eu0, p1 = er1 * eu1;
+                const float inv = rcp(p0 * p1);
+                const float i0 = inv * p1, i1 = inv * p0;                          // 1/p0, 1/p1
+                const float r0 = i0 * eu0, u0 = i0 * er0, r1 = i1 * eu1, u1 = i1 * er1;
+                const float ec0 = 1.0f + ex2(fminf(fmaf(r0, dq[q], dc[q]), 60.f)), ec1 = 1.0f + ex2(fminf(fmaf(r1, dq[q + 1], dc[q + 1]), 60.f));
+                const float ic = rcp(ec0 * ec1);
+                const float c0 = fmaf(-2.0f, ic * ec1, 1.0f), c1 = fmaf(-2.0f, ic * ec0, 1.0f);
+                const float h0 = fmaf(u0, hp[jl] - c0, c0), h1 = fmaf(u1, hp[jl + 1] - c1, c1);
+                hp[jl] = h0;
+                hp[jl + 1] = h1;
                 if (top) {
-                    z0 = fmaf(h, tab[2 * j], z0);
-                    z1 = fmaf(h, tab[2 * j + 1], z1);
+                    z0 = fmaf(h0, tab[2 * j], z0);
+                    z1 = fmaf(h0, tab[2 * j + 1], z1);
+                    z0 = fmaf(h1, tab[2 * j + 2], z0);
+                    z1 = fmaf(h1, tab[2 * j + 3], z1);
                 }
-                if (BASE && live) a.hstore[(((rowbase + n) * L + l) * (size_t)H + j) * Mold + m] = h;
+                if (BASE && live) {
+                    a.hstore[(((rowbase + n) * L + l) * (size_t)H + j) * Mold + m] = h0;
+                    a.hstore[(((rowbase + n) * L + l) * (size_t)H + j + 1) * Mold + m] = h1;
+                }
             }
         }
         // the MMAs of this step are complete: region l can take the new state (it is the h operand of layer l at the next

@@ -116,6 +116,11 @@ def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
     return eloc, logp
 
 
+def tfim_chain_mode(model) -> int:
+    """2: tcgen05 3xFP16 chain kernel, 1: tcgen05 3xTF32, 0: CUDA-core FFMA (see include/rnnwf.h)."""
+    return int(_lib.load().rnnwf_tfim_chain_mode(C.byref(model)))
+
+
 def tfim_diag(model, samples_u8, jz):
     ns = samples_u8.shape[0]
     jz = torch.as_tensor(jz, dtype=torch.float64).reshape(-1).to(samples_u8.device).contiguous()
