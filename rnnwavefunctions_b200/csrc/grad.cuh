@@ -412,7 +412,7 @@ __global__ void wgrad_scatter_kernel(const double* __restrict__ partial, int ksp
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <typename T> inline BwdLaunch choose_bwd_launch(const GruLayout& g) {
+template <typename T> inline BwdLaunch choose_bwd_launch(const GruLayout& g, int64_t rows_hint = 0, int ndir = 1) {
     constexpr int SPT = VT<T>::SPT;
     BwdLaunch best;
     memset(&best, 0, sizeof(best));
@@ -421,7 +421,7 @@ template <typename T> inline BwdLaunch choose_bwd_launch(const GruLayout& g) {
     for (int l = 0; l < g.L; ++l) maxpk = std::max(maxpk, g.pk_size[l]);
     const int dmax = g.L > 1 ? g.H : 0;
     for (int wsm = 1; wsm >= 0; --wsm) {
-        double best_eff = -1.0;
+        double best_eff = -1.0, best_cost = 1e300;
         for (int RT = 1; RT <= 64; ++RT) {
             const int nt = g.CT * RT, M = RT * SPT;
             if (nt > 384 || M > 2 * kHeadThreads) break;
@@ -433,9 +433,17 @@ template <typename T> inline BwdLaunch choose_bwd_launch(const GruLayout& g) {
             if (smem > (size_t)kSmemLimit) break;
             if (fwd > (size_t)kSmemLimit && wsm) break;
             if ((size_t)2 * 64 * (M + 4) * sizeof(T) > (size_t)kSmemLimit) break;   // wgrad_kernel staging tiles (kWgTile = 64)
-            const double eff = (double)nt / (128.0 * (double)((nt + 127) / 128));
-            if (eff >= best_eff - 0.03) {
+            bool take;
+            if (rows_hint > 0) {
+                const double cost = wave_cost(rows_hint, ndir, M);
+                take = cost < best_cost || (cost == best_cost && best.RT > 0 && M > best.M);
+                if (take) best_cost = cost;
+            } else {
+                const double eff = (double)nt / (128.0 * (double)((nt + 127) / 128));
+                take = eff >= best_eff - 0.03;
                 if (eff > best_eff) best_eff = eff;
+            }
+            if (take) {
                 best.CT = g.CT; best.RT = RT; best.M = M; best.Mp = Mp; best.NT = (nt + 31) & ~31;
                 best.w_smem = wsm; best.smem_bytes = (int)smem;
             }
@@ -486,10 +494,10 @@ template <typename T> static GruLaunch fwd_launch_for(const GruLayout& g, const 
 template <typename T> size_t gru_grad_workspace_bytes(const rnnwf_model& m, int64_t ns, int flags) {
     const GruLayout g = make_gru_layout(m);
     const GruLayoutT gt = make_gru_layout_T(g);
-    const BwdLaunch b = choose_bwd_launch<T>(g);
+    const int ndir = (flags & RNNWF_PARITY_SYM) ? 2 : 1;
+    const BwdLaunch b = choose_bwd_launch<T>(g, ns, ndir);
     if (b.RT == 0) return 0;
     const GruLaunch cf = fwd_launch_for<T>(g, b);
-    const int ndir = (flags & RNNWF_PARITY_SYM) ? 2 : 1;
     Ws ws(nullptr, 0);
     carve_grad<T>(ws, g, gt, cf, ndir * cdiv(ns, b.M), m.head == RNNWF_HEAD_COMPLEX, ns);
     return ws.used + 256;
@@ -546,7 +554,7 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
                    double* grad, void* wsp, size_t wsb, cudaStream_t s) {
     const GruLayout g = make_gru_layout(m);
     const GruLayoutT gt = make_gru_layout_T(g);
-    const BwdLaunch b = choose_bwd_launch<T>(g);
+    const BwdLaunch b = choose_bwd_launch<T>(g, ns, (flags & RNNWF_PARITY_SYM) ? 2 : 1);
     RNNWF_CHECK(b.RT > 0, -3, "no backward launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
     const GruLaunch cf = fwd_launch_for<T>(g, b);
     const bool cplx = m.head == RNNWF_HEAD_COMPLEX;

@@ -273,10 +273,11 @@ static int chain_mode(const GruLayout& g) {
 // ---------------------------------------------------------------------------------------------
 template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op, int64_t ns, int flags) {
     const GruLayout g = make_gru_layout(m);
-    const GruLaunch c = choose_gru_launch<T>(g);
+    const int ndir = (flags & RNNWF_PARITY_SYM) ? 2 : 1;
+    const bool one_cta_per_tile = op == RNNWF_OP_SAMPLE || op == RNNWF_OP_LOGPSI;
+    const GruLaunch c = one_cta_per_tile ? choose_gru_launch<T>(g, ns, ndir) : choose_gru_launch<T>(g);
     if (c.RT == 0) return 0;
     const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
-    const int ndir = (flags & RNNWF_PARITY_SYM) ? 2 : 1;
     const int64_t tiles = ndir * cdiv(ns, c.M);
     Ws ws(nullptr, 0);
     switch (op) {
@@ -300,7 +301,7 @@ template <typename T>
 int gru_sample_t(const rnnwf_model& m, const void* params, int64_t ns, uint64_t seed, uint64_t off, uint8_t* out, void* wsp,
                  size_t wsb, cudaStream_t s) {
     const GruLayout g = make_gru_layout(m);
-    const GruLaunch c = choose_gru_launch<T>(g);
+    const GruLaunch c = choose_gru_launch<T>(g, ns, 1);
     RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
     const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
     const int tiles = (int)cdiv(ns, c.M);
@@ -322,7 +323,7 @@ template <typename T>
 int gru_logpsi_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, int flags, double* out, void* wsp,
                  size_t wsb, cudaStream_t s) {
     const GruLayout g = make_gru_layout(m);
-    const GruLaunch c = choose_gru_launch<T>(g);
+    const GruLaunch c = choose_gru_launch<T>(g, ns, (flags & RNNWF_PARITY_SYM) ? 2 : 1);
     RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
     const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
     const int parity = (flags & RNNWF_PARITY_SYM) ? 1 : 0;

@@ -22,12 +22,19 @@ struct Ws {
 // Pick (RT, M) so that CT*RT fills whole groups of 4 warps (one per SM sub-partition) as tightly as
 // possible, the hidden-state tile + resident weights fit in 227 KB of shared memory, and M is as large
 // as possible among near-ties.  Block = compute threads (<= 384) + 4 head warps.
-template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g) {
+// With rows_hint > 0 (one-CTA-per-tile kernels: sampler, log psi, gradient) the tile is instead sized so that the
+// tiles fill the SMs in as few waves as possible: cost = waves * M (time of a tile is proportional to its rows).
+inline double wave_cost(int64_t rows_hint, int ndir, int M, int sms = 148) {
+    const int64_t tiles = ndir * ((rows_hint + M - 1) / M);
+    return (double)((tiles + sms - 1) / sms) * M;
+}
+
+template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g, int64_t rows_hint = 0, int ndir = 1) {
     constexpr int SPT = VT<T>::SPT;
     GruLaunch best;
     memset(&best, 0, sizeof(best));
     for (int wsm = 1; wsm >= 0; --wsm) {
-        double best_eff = -1.0;
+        double best_eff = -1.0, best_cost = 1e300;
         for (int RT = 1; RT <= 64; ++RT) {
             const int nt = g.CT * RT, M = RT * SPT;
             if (nt > 384 || M > 2 * kHeadThreads) break;
@@ -35,9 +42,17 @@ template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g) {
             size_t smem = (wsm ? (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) : 0) + (size_t)g.L * g.H * M * sizeof(T) +
                           2 * (size_t)Mp + 64;
             if (smem > (size_t)kSmemLimit) break;
-            const double eff = (double)nt / (128.0 * (double)((nt + 127) / 128));
-            if (eff >= best_eff - 0.03) {   // near-tie: prefer the larger tile
+            bool take;
+            if (rows_hint > 0) {
+                const double cost = wave_cost(rows_hint, ndir, M);
+                take = cost < best_cost || (cost == best_cost && best.RT > 0 && M > best.M);
+                if (take) best_cost = cost;
+            } else {
+                const double eff = (double)nt / (128.0 * (double)((nt + 127) / 128));
+                take = eff >= best_eff - 0.03;   // near-tie: prefer the larger tile
                 if (eff > best_eff) best_eff = eff;
+            }
+            if (take) {
                 best.CT = g.CT; best.RT = RT; best.M = M; best.Mp = Mp;
                 best.NTc = (nt + 31) & ~31; best.w_smem = wsm; best.smem_bytes = (int)smem;
             }
