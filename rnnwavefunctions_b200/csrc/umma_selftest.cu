@@ -184,7 +184,96 @@ umma_selftest_f16_kernel(int N, int K, const float* __restrict__ A, const float*
     if (warp == 4) umma::tmem_dealloc(tbase, 512);
 }
 
+// TMEM read-bandwidth probe (development aid): `warps` warps (multiple of 4) issue `iters` x (4 x tcgen05.ld x8) each.
+__global__ void __launch_bounds__(544, 1) tmem_ldbw_kernel(int warps, int iters, float* out) {
+    __shared__ uint32_t slot;
+    const int tid = threadIdx.x, warp = tid / 32;
+    if (warp == 16) umma::tmem_alloc(&slot, 512);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = slot;
+    float acc = 0.f;
+    long long t0 = 0, t1 = 0;
+    if (warp < warps) {
+        const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 32);
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < 32; c += 8) umma::tmem_st8(lane_addr + c, z);
+        umma::wait_st();
+        t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            float a[8], b[8], c[8], d[8];
+            umma::tmem_ld8(lane_addr, a);
+            umma::tmem_ld8(lane_addr + 8, b);
+            umma::tmem_ld8(lane_addr + 16, c);
+            umma::tmem_ld8(lane_addr + 24, d);
+            umma::wait_ld();
+            acc += a[0] + b[1] + c[2] + d[3];
+        }
+        t1 = clock64();
+    }
+    __syncthreads();
+    if (tid == 0) printf("[tmem ld probe] %d warps x %d x 4 ld8: %lld cycles -> %.1f B/cycle/SM\n", warps, iters, t1 - t0,
+                         (double)warps * iters * 4 * 1024.0 / (double)(t1 - t0));
+    if (acc == 123.f) out[0] = acc;
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 16) umma::tmem_dealloc(tbase, 512);
+}
+
+// MMA cost probe (development aid): `count` back-to-back kind::f16 MMAs of M=128, N, K=16 on zeroed operands.
+__global__ void __launch_bounds__(160, 1) mma_cost_kernel(int N, int count, float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint32_t slot;
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    if (warp == 4) umma::tmem_alloc(&slot, 512);
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); }
+    for (int i = tid; i < 256 * 16 * 2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = slot;
+    if (warp < 4) {
+        const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        umma::tmem_st8(lane_addr + 300, z);
+        umma::wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4 && lane == 0) {
+        umma::fence_after_sync();
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t bd = umma::smem_desc(umma::smem_u32(smem), 128, 256);
+        const long long t0 = clock64();
+        for (int i = 0; i < count; ++i) umma::mma_f16_ts(tbase, tbase + 300, bd, idesc, i > 0);
+        const long long t1 = clock64();
+        umma::commit(&bar);
+        umma::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        printf("[mma cost] N=%3d: %d MMAs issue %lld cycles, complete %lld cycles -> %.1f cycles/MMA\n", N, count, t1 - t0, t2 - t0,
+               (double)(t2 - t0) / count);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) umma::tmem_dealloc(tbase, 512);
+    if (out == nullptr) return;
+}
+
 int umma_selftest_f16_impl(int N, int K, const float* A, const float* B, float* D, int passes, int dcol, cudaStream_t s) {
+    if (passes == 2 && dcol >= 100) {   // development aid: MMA cost probe, N = dcol - 100
+        RNNWF_CUDA(cudaFuncSetAttribute(mma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
+        mma_cost_kernel<<<1, 160, 16384, s>>>(dcol - 100, 400, D);
+        RNNWF_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (passes == 2) {   // development aid: TMEM read-bandwidth probe with dcol warps
+        tmem_ldbw_kernel<<<1, 544, 0, s>>>(dcol, 2000, D);
+        RNNWF_CUDA(cudaGetLastError());
+        return 0;
+    }
     RNNWF_CHECK(N >= 16 && N <= 256 && N % 16 == 0 && K >= 1 && K <= 64 && (passes == 1 || passes == 3) && dcol >= 0 && dcol + N <= 300, -1,
                 "umma f16 selftest: bad shape");
     const int Kp = (K + 15) & ~15;

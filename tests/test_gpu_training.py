@@ -99,6 +99,21 @@ def test_run_1dtfim_converges_to_exact(tmp_path, golden):
     assert len(E2) == 521 and np.allclose(E2[:501], E[:501])
 
 
+def test_run_1dtfim_tensor_core_path_converges(tmp_path):
+    # 50 units: rnnwf_tfim_eloc runs the tcgen05 3xFP16 chain kernel; the optimisation must reach the free-fermion ground state
+    from rnnwavefunctions_b200 import ops
+    N = 16
+    model = ops.make_model(num_layers=2, units=50, n_sites=N)
+    assert ops.tfim_chain_mode(model) == 2
+    exact = O.tfim1d_exact_energy(N, 1.0, 1.0)
+    E, V = TR.run_1DTFIM(numsteps=400, systemsize=N, num_units=50, Bx=1, num_layers=2, numsamples=500, learningrate=5e-3, seed=7,
+                         save=False, verbose=False)
+    last = np.mean(E[-50:])
+    assert abs(last - exact) < 0.05, (last, exact)
+    assert last > exact - 0.02
+    assert np.mean(V[-50:]) < 0.2
+
+
 def test_run_1dtfim_parity_and_multilayer(tmp_path, golden):
     exact = float(golden("known_answers")["tfim_N8"])
     E, V = TR.run_1DTFIM(numsteps=500, systemsize=8, num_units=8, Bx=1, num_layers=2, numsamples=400, learningrate=1e-2, seed=3,
