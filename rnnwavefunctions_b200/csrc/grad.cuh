@@ -372,6 +372,92 @@ __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs<T> a, double* __re
             partial[((size_t)ks * Rp + r0 + tr * 4 + i) * Cp + c0 + tc * 4 + j] = accd[i][j];
 }
 
+// FP32 fast path of the same reduction: one block computes the WHOLE [R x cols] output for its chunk of (tile, site)
+// blocks, so every A / B element is read from HBM once (the tiled kernel above re-reads them rtiles*ctiles times).
+// 288 threads, thread tile 8 x 10 (80 FP32 accumulators); every kWgFlush blocks the tile is flushed into the block's own
+// FP64 partial (deterministic: no atomics, fixed order).
+constexpr int kWgfThreads = 288, kWgfTr = 8, kWgfTc = 10, kWgFlush = 32;
+
+__global__ void __launch_bounds__(kWgfThreads) wgrad_fast_kernel(WgradArgs<float> a, double* __restrict__ partial, int Rp, int Cp) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int M = a.M, MS = M + 4;
+    const int R = a.rows0 + a.rows1 + 1;
+    const int RG = (R + kWgfTr - 1) / kWgfTr, CG = (a.cols + kWgfTc - 1) / kWgfTc;
+    float* As = reinterpret_cast<float*>(smem);                     // [RG * 8][MS]
+    float* Bs = As + (size_t)RG * kWgfTr * MS;                       // [CG * 10][MS]
+    const int tid = threadIdx.x;
+    const bool active = tid < RG * CG;
+    const int tr = tid / CG, tc = tid % CG;
+    const int ks = blockIdx.x;
+    const int64_t b0 = a.nblk * ks / a.ksplit, b1 = a.nblk * (ks + 1) / a.ksplit;
+    double* out = partial + (size_t)ks * Rp * Cp;
+    for (int i = tid; i < Rp * Cp; i += blockDim.x) out[i] = 0.0;
+    float acc[kWgfTr][kWgfTc];
+#pragma unroll
+    for (int i = 0; i < kWgfTr; ++i)
+#pragma unroll
+        for (int j = 0; j < kWgfTc; ++j) acc[i][j] = 0.f;
+    int pending = 0;
+    __syncthreads();
+    for (int64_t blk = b0; blk < b1; ++blk) {
+        const int n = (int)(blk % a.N);
+        for (int i = tid; i < (RG * kWgfTr + CG * kWgfTc) * (M / 4); i += blockDim.x) {
+            const int row = i / (M / 4), m4 = (i % (M / 4)) * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (row < RG * kWgfTr) {
+                const int r = row;
+                if (r < a.rows0) {
+                    if (a.xmode == 1) ldv<4>(v, a.hstore + ((blk * a.L + a.lx) * a.H + r) * M + m4);
+                    else if (n > 0) {
+                        for (int q = 0; q < 4; ++q) v[q] = a.sigT[(blk - 1) * M + m4 + q] == r ? 1.f : 0.f;
+                    }
+                } else if (r < a.rows0 + a.rows1) {
+                    if (!(a.hshift && n == 0)) ldv<4>(v, a.hstore + (((blk - a.hshift) * a.L + a.lh) * a.H + (r - a.rows0)) * M + m4);
+                } else if (r == R - 1) {
+                    v[0] = v[1] = v[2] = v[3] = 1.f;
+                }
+                stv<4>(As + (size_t)row * MS + m4, v);
+            } else {
+                const int c = row - RG * kWgfTr;
+                if (c < a.cols) ldv<4>(v, a.B + (blk * a.cols + c) * M + m4);
+                stv<4>(Bs + (size_t)c * MS + m4, v);
+            }
+        }
+        __syncthreads();
+        if (active) {
+            const float* ap = As + (size_t)tr * kWgfTr * MS;
+            const float* bp = Bs + (size_t)tc * kWgfTc * MS;
+            for (int m4 = 0; m4 < M; m4 += 4) {
+                float av[kWgfTr][4], bv[kWgfTc][4];
+#pragma unroll
+                for (int i = 0; i < kWgfTr; ++i) ldv<4>(av[i], ap + (size_t)i * MS + m4);
+#pragma unroll
+                for (int j = 0; j < kWgfTc; ++j) ldv<4>(bv[j], bp + (size_t)j * MS + m4);
+#pragma unroll
+                for (int i = 0; i < kWgfTr; ++i)
+#pragma unroll
+                    for (int j = 0; j < kWgfTc; ++j)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) acc[i][j] = fmaf(av[i][q], bv[j][q], acc[i][j]);
+            }
+        }
+        if (++pending == kWgFlush || blk + 1 == b1) {
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < kWgfTr; ++i)
+#pragma unroll
+                    for (int j = 0; j < kWgfTc; ++j) {
+                        const int r = tr * kWgfTr + i, c = tc * kWgfTc + j;
+                        if (r < Rp && c < Cp) out[(size_t)r * Cp + c] += (double)acc[i][j];
+                        acc[i][j] = 0.f;
+                    }
+            }
+            pending = 0;
+        }
+        __syncthreads();
+    }
+}
+
 // sum the split-K partials (fixed order) and scatter into the flat gradient.
 //   layer mode : rows [x (d) | h (H) | ones], cols [da_r (H) | da_u (H) | da_c (H) | dq (H)]
 //   head mode  : rows [h_top (H) | ones],     cols [dz (2) | dz_phase (2)]
@@ -477,7 +563,7 @@ static GradWs<T> carve_grad(Ws& ws, const GruLayout& g, const GruLayoutT& gt, co
     w.Rp = (int)cdiv(R, kWgTile) * kWgTile;
     w.Cp = (int)cdiv(C, kWgTile) * kWgTile;
     const int ntile = (w.Rp / kWgTile) * (w.Cp / kWgTile);
-    w.ksplit = (int)std::max<int64_t>(1, std::min<int64_t>((148 * 4 + ntile - 1) / ntile, tiles * g.N));
+    w.ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::is_same<T, float>::value ? 296 : (148 * 4 + ntile - 1) / ntile, tiles * g.N));
     w.partial = ws.take<double>((size_t)w.ksplit * w.Rp * w.Cp);
     return w;
 }
@@ -538,11 +624,25 @@ static int launch_wgrad(const GruLayout& g, const GradWs<T>& w, int M, int64_t n
     a.rtiles = (int)cdiv(R, kWgTile);
     a.ctiles = (int)cdiv(a.cols, kWgTile);
     a.ksplit = w.ksplit;
-    const int smem = 2 * kWgTile * (M + 4) * (int)sizeof(T);
-    auto k = wgrad_kernel<T>;
-    if (int e = set_smem(k, smem)) return e;
-    prof_count(); k<<<dim3(a.rtiles * a.ctiles, a.ksplit), 256, smem, s>>>(a, w.partial);
-    RNNWF_CUDA(cudaGetLastError());
+    bool fast = false;
+    if constexpr (std::is_same<T, float>::value) {
+        const int RG = (R + kWgfTr - 1) / kWgfTr, CG = (a.cols + kWgfTc - 1) / kWgfTc;
+        const size_t fsmem = (size_t)(RG * kWgfTr + CG * kWgfTc) * (M + 4) * sizeof(float);
+        if (RG * CG <= kWgfThreads && fsmem <= (size_t)kSmemLimit && RG * kWgfTr <= a.rtiles * kWgTile + 0 && !getenv("RNNWF_WGRAD_TILED")) {
+            fast = true;
+            auto k = wgrad_fast_kernel;
+            if (int e = set_smem(k, (int)fsmem)) return e;
+            prof_count(); k<<<a.ksplit, kWgfThreads, fsmem, s>>>(a, w.partial, a.rtiles * kWgTile, a.ctiles * kWgTile);
+            RNNWF_CUDA(cudaGetLastError());
+        }
+    }
+    if (!fast) {
+        const int smem = 2 * kWgTile * (M + 4) * (int)sizeof(T);
+        auto k = wgrad_kernel<T>;
+        if (int e = set_smem(k, smem)) return e;
+        prof_count(); k<<<dim3(a.rtiles * a.ctiles, a.ksplit), 256, smem, s>>>(a, w.partial);
+        RNNWF_CUDA(cudaGetLastError());
+    }
     prof_count(); wgrad_scatter_kernel<<<grid_for((int64_t)R * a.cols), 256, 0, s>>>(w.partial, a.ksplit, a.rtiles * kWgTile, a.ctiles * kWgTile, g, l,
                                                                     head ? 1 : 0, grad);
     RNNWF_CUDA(cudaGetLastError());

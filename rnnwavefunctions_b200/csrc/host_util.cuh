@@ -23,10 +23,10 @@ struct Ws {
 // possible, the hidden-state tile + resident weights fit in 227 KB of shared memory, and M is as large
 // as possible among near-ties.  Block = compute threads (<= 384) + 4 head warps.
 // With rows_hint > 0 (one-CTA-per-tile kernels: sampler, log psi, gradient) the tile is instead sized so that the
-// tiles fill the SMs in as few waves as possible: cost = waves * M (time of a tile is proportional to its rows).
+// tiles fill the SMs in as few waves as possible: cost = waves * (M + 24) (per-site time of a tile = fixed part + rows).
 inline double wave_cost(int64_t rows_hint, int ndir, int M, int sms = 148) {
     const int64_t tiles = ndir * ((rows_hint + M - 1) / M);
-    return (double)((tiles + sms - 1) / sms) * M;
+    return (double)((tiles + sms - 1) / sms) * (M + 24);   // + a fixed per-site cost worth ~24 rows (measured: tiny tiles are inefficient)
 }
 
 template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g, int64_t rows_hint = 0, int ndir = 1) {
