@@ -192,7 +192,7 @@ struct Args {
 // one (site, layer) step of a row thread: wait for the MMAs, gate math on the accumulators, stage the new state
 template <int H, int PART, bool BASE>
 __device__ __forceinline__ void row_step(const Args& a, const float* tab, float2* zsm, uint64_t* bar, uint32_t& par, uint32_t lane_addr,
-                                         int rowi, bool live, size_t rowbase, int m, int n, int l, float* hp, double& acc, int sg, double lsel) {
+                                         int rowi, bool live, size_t rowbase, int m, int n, int l, float* hp, float2& zout) {
     using P = Part<H, PART>;
     const int L = a.g.L, Mold = a.Mold;
     const bool top = l == L - 1;
@@ -246,23 +246,9 @@ __device__ __forceinline__ void row_step(const Args& a, const float* tab, float2
         if (cnt == 8) stage_units<8>(reg, P::U0 + 8 * gq, hp + 8 * gq);
         else stage_units<2>(reg, P::U0 + 8 * gq, hp + 8 * gq);
     }
-    if (top) {
+    if (top) {   // partial head sums; the log-softmax itself is finished during the next step's MMA wait (row_chain)
         if (PART == 1) zsm[rowi] = make_float2(z0, z1);
-        row_sync();
-        if (PART == 0 && live) {
-            const float2 o = zsm[rowi];
-            const float f0 = z0 + o.x + tab[128], f1 = z1 + o.y + tab[129];
-            // log softmax of the 2-way head in FP32 (log1pf/expf, ~1e-7 relative); the site terms are summed in FP64
-            const float dsel = sg ? f0 - f1 : f1 - f0;                             // z_other - z_selected
-            const double ls = dsel > 30.f ? -(double)dsel : -(double)log1pf(expf(dsel));
-            if (BASE) {
-                a.la_sel[(rowbase + n) * Mold + m] = ls;
-                a.la_oth[(rowbase + n) * Mold + m] = -dsel > 30.f ? (double)dsel : -(double)log1pf(expf(-dsel));
-                acc += ls;
-            } else {
-                acc += ls - lsel;
-            }
-        }
+        else zout = make_float2(z0, z1);
     }
 }
 
@@ -296,6 +282,27 @@ __device__ __forceinline__ void row_chain(const Args& a, const float* tab, float
         return c;
     };
     int code = PART == 0 ? fetch_code(s + 1) : 2;
+    // head of the previous site, finished while the MMAs of the next step run (part 0 only)
+    float2 pz = make_float2(0.f, 0.f);
+    int psg = 0, pn = -1;
+    double plsel = 0.0;
+    auto finish_head = [&]() {
+        if (PART == 0 && pn >= 0 && live) {
+            const float2 o = zsm[rowi];
+            const float f0 = pz.x + o.x + tab[128], f1 = pz.y + o.y + tab[129];
+            // log softmax of the 2-way head in FP32 (log1pf/expf, ~1e-7 relative); the site terms are summed in FP64
+            const float dsel = psg ? f0 - f1 : f1 - f0;                             // z_other - z_selected
+            const double ls = dsel > 30.f ? -(double)dsel : -(double)log1pf(expf(dsel));
+            if (BASE) {
+                a.la_sel[(rowbase + pn) * Mold + m] = ls;
+                a.la_oth[(rowbase + pn) * Mold + m] = -dsel > 30.f ? (double)dsel : -(double)log1pf(expf(-dsel));
+                acc += ls;
+            } else {
+                acc += ls - plsel;
+            }
+        }
+        pn = -1;
+    };
     for (int n = s + 1; n < N; ++n) {
         // ---- layer 0: one-hot input of the previous spin ----
         if (PART == 0) {
@@ -304,7 +311,7 @@ __device__ __forceinline__ void row_chain(const Args& a, const float* tab, float
         }
         umma::wait_st();
         umma::fence_before_sync();
-        named_sync();
+        named_sync();                      // also orders part 1's head partials (zsm) of the previous site before finish_head
         int sg = 0;
         double lsel = 0.0;
         if (PART == 0) {
@@ -313,21 +320,26 @@ __device__ __forceinline__ void row_chain(const Args& a, const float* tab, float
                 sg = a.sigT[(rowbase + n) * Mold + m];
                 if (!BASE) lsel = a.la_sel[(rowbase + n) * Mold + m];
             }
+            finish_head();
         }
-        row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 0, hp0, acc, sg, lsel);
+        float2 z = make_float2(0.f, 0.f);
+        row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 0, hp0, z);
         if (L > 1) {
             umma::wait_st();
             umma::fence_before_sync();
             named_sync();
-            row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 1, hp1, acc, sg, lsel);
+            row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 1, hp1, z);
         }
         if (L > 2) {
             umma::wait_st();
             umma::fence_before_sync();
             named_sync();
-            row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 2, hp2, acc, sg, lsel);
+            row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 2, hp2, z);
         }
+        pz = z; psg = sg; plsel = lsel; pn = n;
     }
+    row_sync();                            // part 1's partials of the last site
+    finish_head();
 }
 
 template <int H, bool BASE>
