@@ -288,7 +288,11 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
             if (std::is_same<T, float>::value && tc_supported(g)) carve_tc(ws, g, make_tc_layout(g), 160);
             if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
             break;
-        case RNNWF_OP_J1J2_ELOC: carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns); ws.take<float>((size_t)ns * (2 * g.N + 1)); break;
+        case RNNWF_OP_J1J2_ELOC:
+            carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns);
+            ws.take<float>((size_t)ns * (2 * g.N + 1));
+            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
+            break;
         case RNNWF_OP_VMC_GRAD: return gru_grad_workspace_bytes<T>(m, ns, flags);
         default: return 0;
     }

@@ -44,13 +44,13 @@ inline Layout make_layout(const GruLayout& g) {
     t.l1_bytes = 2 * t.bh_bytes + 2 * t.bx_bytes;
     t.zero_off = t.l0_bytes + (g.L - 1) * t.l1_bytes;
     t.tab_off = t.zero_off + 64 * 16 * 2;
-    t.tab_floats = 2 * 64 + 4;
+    t.tab_floats = g.nheads * (2 * 64 + 4);   // per head: Wd[64][2] | bd[2] | pad
     t.img_bytes = t.tab_off + t.tab_floats * 4;
     return t;
 }
 
 inline bool supported(const GruLayout& g) {
-    if (!(g.H == 50 && g.nheads == 1 && g.N >= 2 && g.L >= 1 && g.L <= 3)) return false;
+    if (!(g.H == 50 && g.N >= 2 && g.L >= 1 && g.L <= 3)) return false;
     return make_layout(g).img_bytes + 2048 <= kSmemLimit;
 }
 
@@ -116,9 +116,11 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < tail; idx += gridDim.x * blockDim.x) {
         float v = 0.f;
         const int q = idx - (t.tab_off - t.zero_off) / 4;
-        if (q >= 0) {                                   // head: Wd[j][2] (64 x 2) | bd[2]
-            if (q < 128) { if (q / 2 < H) v = flat[g.flat_head + q]; }
-            else if (q < 130) v = flat[g.flat_head + 2 * H + (q - 128)];
+        if (q >= 0) {                                   // per head: Wd[j][2] (64 x 2) | bd[2] | pad
+            const int hd = q / 132, r = q % 132;
+            const float* hw = flat + g.flat_head + hd * (2 * H + 2);
+            if (r < 128) { if (r / 2 < H) v = hw[r]; }
+            else if (r < 130) v = hw[2 * H + (r - 128)];
         }
         reinterpret_cast<float*>(img + t.zero_off)[idx] = v;
     }
@@ -187,12 +189,17 @@ struct Args {
     double* lp;               // BASE: sum_n la_sel
     double* delta;            // FLIP: [tile][slot][M]
     int* counter;
+    // complex cRNN / J1-J2 exchanges (CPLX instantiations): phases, imaginary parts, slot plan
+    double *ph_sel, *ph_oth, *lp_im, *delta_im;
+    const int* order;         // slots by decreasing chain length
+    const double *j1, *j2;    // couplings: slots with a zero coupling are skipped (J1J2/TrainingRNN_J1J2.py:69,84)
+    int n_kind1, n_kind2, nslots;
 };
 
 // one (site, layer) step of a row thread: wait for the MMAs, gate math on the accumulators, stage the new state
-template <int H, int PART, bool BASE>
-__device__ __forceinline__ void row_step(const Args& a, const float* tab, float2* zsm, uint64_t* bar, uint32_t& par, uint32_t lane_addr,
-                                         int rowi, bool live, size_t rowbase, int m, int n, int l, float* hp, float2& zout) {
+template <int H, int PART, bool BASE, bool CPLX>
+__device__ __forceinline__ void row_step(const Args& a, const float* tab, float4* zsm, uint64_t* bar, uint32_t& par, uint32_t lane_addr,
+                                         int rowi, bool live, size_t rowbase, int m, int n, int l, float* hp, float4& zout) {
     using P = Part<H, PART>;
     const int L = a.g.L, Mold = a.Mold;
     const bool top = l == L - 1;
@@ -200,7 +207,7 @@ __device__ __forceinline__ void row_step(const Args& a, const float* tab, float2
     par ^= 1;
     umma::fence_after_sync();
     const uint32_t reg = lane_addr + kColR + 64 * l;
-    float z0 = 0.f, z1 = 0.f;
+    float z0 = 0.f, z1 = 0.f, y0 = 0.f, y1 = 0.f;
 #pragma unroll
     for (int gq = 0; gq < P::NG; ++gq) {
         const int cnt = P::U - 8 * gq >= 8 ? 8 : P::U - 8 * gq;
@@ -234,6 +241,12 @@ __device__ __forceinline__ void row_step(const Args& a, const float* tab, float2
                     z1 = fmaf(h0, tab[2 * j + 1], z1);
                     z0 = fmaf(h1, tab[2 * j + 2], z0);
                     z1 = fmaf(h1, tab[2 * j + 3], z1);
+                    if (CPLX) {
+                        y0 = fmaf(h0, tab[132 + 2 * j], y0);
+                        y1 = fmaf(h0, tab[132 + 2 * j + 1], y1);
+                        y0 = fmaf(h1, tab[132 + 2 * j + 2], y0);
+                        y1 = fmaf(h1, tab[132 + 2 * j + 3], y1);
+                    }
                 }
                 if (BASE && live) {
                     a.hstore[(((rowbase + n) * L + l) * (size_t)H + j) * Mold + m] = h0;
@@ -247,14 +260,16 @@ __device__ __forceinline__ void row_step(const Args& a, const float* tab, float2
         else stage_units<2>(reg, P::U0 + 8 * gq, hp + 8 * gq);
     }
     if (top) {   // partial head sums; the log-softmax itself is finished during the next step's MMA wait (row_chain)
-        if (PART == 1) zsm[rowi] = make_float2(z0, z1);
-        else zout = make_float2(z0, z1);
+        if (PART == 1) zsm[rowi] = make_float4(z0, z1, y0, y1);
+        else zout = make_float4(z0, z1, y0, y1);
     }
 }
 
-template <int H, int PART, bool BASE>
-__device__ __forceinline__ void row_chain(const Args& a, const float* tab, float2* zsm, uint64_t* bars, uint32_t& par, uint32_t lane_addr,
-                                          int rowi, bool live, size_t rowbase, int m, int s, double& acc) {
+// all row-thread work of one chain.  kind 0: sigma with site s flipped (TFIM); kind 1 / 2: sites s and t = s + kind exchanged
+// (J1-J2, J1J2/TrainingRNN_J1J2.py:68-92); BASE: the unmodified configuration from site 0 (s = -1).
+template <int H, int PART, bool BASE, bool CPLX>
+__device__ __forceinline__ void row_chain(const Args& a, const float* tab, float4* zsm, uint64_t* bars, uint32_t& par, uint32_t lane_addr,
+                                          int rowi, bool live, size_t rowbase, int m, int s, int t, double& acc, double& acc_im) {
     using P = Part<H, PART>;
     const int L = a.g.L, N = a.g.N, Mold = a.Mold;
     float hp0[P::U], hp1[P::U], hp2[P::U];
@@ -273,32 +288,57 @@ __device__ __forceinline__ void row_chain(const Args& a, const float* tab, float
     if (L > 1) stage_all<H, PART>(lane_addr + kColR + 64, hp1);
     if (L > 2) stage_all<H, PART>(lane_addr + kColR + 128, hp2);
     const uint32_t x0 = lane_addr + kColR + 64 * L;
-    auto fetch_code = [&](int n) {
-        int c = 2;
-        if (live && n > 0) {
-            c = a.sigT[(rowbase + n - 1) * Mold + m];
-            if (!BASE && n - 1 == s) c = 1 - c;
-        }
+    auto spin = [&](int q) {   // spin of site q in the configuration this chain evaluates
+        int c = a.sigT[(rowbase + q) * Mold + m];
+        if (!BASE && (q == s || q == t)) c = 1 - c;
         return c;
     };
-    int code = PART == 0 ? fetch_code(s + 1) : 2;
+    int code = (PART == 0 && live && s >= 0) ? spin(s) : 2;                // input of site s + 1 (the zero vector at site 0)
+    int nup = 0;                                                           // up spins among the sites before the current one
+    if (CPLX && PART == 0 && live && !BASE) {
+        for (int q = 0; q < s; ++q) nup += a.sigT[(rowbase + q) * Mold + m];
+        nup += code;
+    }
     // head of the previous site, finished while the MMAs of the next step run (part 0 only)
-    float2 pz = make_float2(0.f, 0.f);
+    float4 pz = make_float4(0.f, 0.f, 0.f, 0.f);
     int psg = 0, pn = -1;
-    double plsel = 0.0;
     auto finish_head = [&]() {
         if (PART == 0 && pn >= 0 && live) {
-            const float2 o = zsm[rowi];
+            const float4 o = zsm[rowi];
             const float f0 = pz.x + o.x + tab[128], f1 = pz.y + o.y + tab[129];
             // log softmax of the 2-way head in FP32 (log1pf/expf, ~1e-7 relative); the site terms are summed in FP64
             const float dsel = psg ? f0 - f1 : f1 - f0;                             // z_other - z_selected
-            const double ls = dsel > 30.f ? -(double)dsel : -(double)log1pf(expf(dsel));
+            double ls = dsel > 30.f ? -(double)dsel : -(double)log1pf(expf(dsel));
+            double lo = -dsel > 30.f ? (double)dsel : -(double)log1pf(expf(-dsel));
+            double ps = 0.0, po = 0.0;
+            if (CPLX) {
+                // amplitude = sqrt(softmax) with the zero-magnetisation mask and renormalisation
+                // (J1J2/ComplexRNNwavefunction.py:85-93,147-155); phase = pi * softsign (:8-9)
+                ls *= 0.5;
+                lo *= 0.5;
+                if (2 * pn >= N) {
+                    const int half = N / 2, ndn = pn - nup;
+                    const bool ok_dn = (half - 1 - ndn) >= 0, ok_up = (half - 1 - nup) >= 0;
+                    const bool ok_sel = psg ? ok_up : ok_dn, ok_oth = psg ? ok_dn : ok_up;
+                    const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+                    if (!ok_sel) ls = ninf; else if (!ok_oth) ls = 0.0;
+                    if (!ok_oth) lo = ninf; else if (!ok_sel) lo = 0.0;
+                }
+                const float y0 = pz.z + o.z + tab[132 + 128], y1 = pz.w + o.w + tab[132 + 129];
+                const double ys = psg ? (double)y1 : (double)y0, yo = psg ? (double)y0 : (double)y1;
+                ps = kPi * ys / (1.0 + fabs(ys));
+                po = kPi * yo / (1.0 + fabs(yo));
+                nup += psg;
+            }
+            const size_t o_ = (rowbase + pn) * Mold + m;
             if (BASE) {
-                a.la_sel[(rowbase + pn) * Mold + m] = ls;
-                a.la_oth[(rowbase + pn) * Mold + m] = -dsel > 30.f ? (double)dsel : -(double)log1pf(expf(-dsel));
+                a.la_sel[o_] = ls;
+                a.la_oth[o_] = lo;
                 acc += ls;
+                if (CPLX) { a.ph_sel[o_] = ps; a.ph_oth[o_] = po; acc_im += ps; }
             } else {
-                acc += ls - plsel;
+                acc += ls - a.la_sel[o_];
+                if (CPLX) acc_im += ps - a.ph_sel[o_];
             }
         }
         pn = -1;
@@ -313,41 +353,39 @@ __device__ __forceinline__ void row_chain(const Args& a, const float* tab, float
         umma::fence_before_sync();
         named_sync();                      // also orders part 1's head partials (zsm) of the previous site before finish_head
         int sg = 0;
-        double lsel = 0.0;
         if (PART == 0) {
-            if (n + 1 < N) code = fetch_code(n + 1);
             if (live) {
-                sg = a.sigT[(rowbase + n) * Mold + m];
-                if (!BASE) lsel = a.la_sel[(rowbase + n) * Mold + m];
+                sg = spin(n);
+                code = sg;
             }
             finish_head();
         }
-        float2 z = make_float2(0.f, 0.f);
-        row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 0, hp0, z);
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        row_step<H, PART, BASE, CPLX>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 0, hp0, z);
         if (L > 1) {
             umma::wait_st();
             umma::fence_before_sync();
             named_sync();
-            row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 1, hp1, z);
+            row_step<H, PART, BASE, CPLX>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 1, hp1, z);
         }
         if (L > 2) {
             umma::wait_st();
             umma::fence_before_sync();
             named_sync();
-            row_step<H, PART, BASE>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 2, hp2, z);
+            row_step<H, PART, BASE, CPLX>(a, tab, zsm, &bars[0], par, lane_addr, rowi, live, rowbase, m, n, 2, hp2, z);
         }
-        pz = z; psg = sg; plsel = lsel; pn = n;
+        pz = z; psg = sg; pn = n;
     }
     row_sync();                            // part 1's partials of the last site
     finish_head();
 }
 
-template <int H, bool BASE>
+template <int H, bool BASE, bool CPLX>
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(128) unsigned char smem_h16[];
     const Layout& t = a.t;
     const float* tab = reinterpret_cast<const float*>(smem_h16 + t.tab_off);
-    float2* zsm = reinterpret_cast<float2*>(smem_h16 + ((t.img_bytes + 15) & ~15));
+    float4* zsm = reinterpret_cast<float4*>(smem_h16 + ((t.img_bytes + 15) & ~15));
     uint64_t* bars = reinterpret_cast<uint64_t*>(zsm + kRows);              // [0] MMAs, [1] weight image
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     int* s_work = reinterpret_cast<int*>(tmem_slot + 1);
@@ -383,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     }
     if (is_row) umma::mbar_wait(&bars[1], 0);                               // tab is read with ordinary loads
     uint32_t par = 0;
-    const int total = (BASE ? 1 : N) * a.tiles128;
+    const int total = (BASE ? 1 : a.nslots) * a.tiles128;
     const uint32_t idN = (1u << 4) | ((uint32_t)(kNN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);     // F16 x F16 -> F32, M = 128
     const uint32_t idZ = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t sB = umma::smem_u32(smem_h16);
@@ -395,18 +433,29 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         const int work = *s_work;
         __syncthreads();
         if (work >= total) break;
-        const int s = BASE ? -1 : work / a.tiles128, tile = work % a.tiles128;   // ascending s = longest chains first
+        const int tile = work % a.tiles128;
+        int slot = 0, s = -1, tt = -1;                                        // modified sites of this chain (none for BASE)
+        if (!BASE) {
+            slot = a.order ? a.order[work / a.tiles128] : work / a.tiles128;  // decreasing chain length
+            if (slot < a.nslots - a.n_kind1 - a.n_kind2) s = slot;
+            else if (slot < a.nslots - a.n_kind2) { s = slot - (a.nslots - a.n_kind1 - a.n_kind2); tt = s + 1; }
+            else { s = slot - (a.nslots - a.n_kind2); tt = s + 2; }
+            if (tt >= 0 && ((tt == s + 1 && a.j1 && a.j1[s] == 0.0) || (tt == s + 2 && a.j2 && a.j2[s] == 0.0))) continue;
+        }
         const int64_t R = (int64_t)tile * kRows + rowi;
         const bool live = is_row && R < a.rows_total;
         const int64_t t120 = live ? R / Mold : 0;
         const int m = live ? (int)(R % Mold) : 0;
         const size_t rowbase = (size_t)t120 * N;                            // index of (old tile, site 0)
-        double acc = 0.0;
-        if (!BASE && live && part == 0) acc = a.la_oth[(rowbase + s) * Mold + m] - a.la_sel[(rowbase + s) * Mold + m];
+        double acc = 0.0, acc_im = 0.0;
+        if (!BASE && live && part == 0) {
+            acc = a.la_oth[(rowbase + s) * Mold + m] - a.la_sel[(rowbase + s) * Mold + m];
+            if (CPLX) acc_im = a.ph_oth[(rowbase + s) * Mold + m] - a.ph_sel[(rowbase + s) * Mold + m];
+        }
 
         if (is_row) {
-            if (part == 0) row_chain<H, 0, BASE>(a, tab, zsm, bars, par, lane_addr, rowi, live, rowbase, m, s, acc);
-            else row_chain<H, 1, BASE>(a, tab, zsm, bars, par, lane_addr, rowi, live, rowbase, m, s, acc);
+            if (part == 0) row_chain<H, 0, BASE, CPLX>(a, tab, zsm, bars, par, lane_addr, rowi, live, rowbase, m, s, tt, acc, acc_im);
+            else row_chain<H, 1, BASE, CPLX>(a, tab, zsm, bars, par, lane_addr, rowi, live, rowbase, m, s, tt, acc, acc_im);
         } else {
             for (int n = s + 1; n < N; ++n) {
                 for (int l = 0; l < L; ++l) {
@@ -453,8 +502,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             }
         }
         if (live && part == 0) {
-            if (BASE) a.lp[t120 * Mold + m] = acc;
-            else a.delta[((size_t)t120 * N + s) * Mold + m] = acc;
+            if (BASE) {
+                a.lp[t120 * Mold + m] = acc;
+                if (CPLX) a.lp_im[t120 * Mold + m] = acc_im;
+            } else {
+                a.delta[((size_t)t120 * a.nslots + slot) * Mold + m] = acc;
+                if (CPLX) a.delta_im[((size_t)t120 * a.nslots + slot) * Mold + m] = acc_im;
+            }
         }
     }
     umma::fence_before_sync();
@@ -462,36 +516,25 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     if (warp == 8) umma::tmem_dealloc(tbase, 512);
 }
 
-inline size_t smem_bytes(const Layout& t) { return (size_t)((t.img_bytes + 15) & ~15) + kRows * sizeof(float2) + 64; }
+inline size_t smem_bytes(const Layout& t) { return (size_t)((t.img_bytes + 15) & ~15) + kRows * sizeof(float4) + 64; }
 
-// base pass + single-flip chains (replaces launch_forward<STASH> + launch_chain for the FP32 pRNN with 50 units)
-static int launch_eloc(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
-                       double* la_sel, double* la_oth, double* lp, double* delta, int* counter, bool flips, cudaStream_t s) {
-    const Layout t = make_layout(g);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    Args a;
-    a.g = g; a.t = t; a.Mold = Mold;
-    a.rows_total = (int64_t)tiles * Mold;
-    a.tiles128 = (int)cdiv(a.rows_total, kRows);
-    a.img = img; a.sigT = sigT; a.hstore = hstore; a.la_sel = la_sel; a.la_oth = la_oth; a.lp = lp; a.delta = delta; a.counter = counter;
-    const int smem = (int)smem_bytes(t);
+template <bool CPLX>
+static int launch_chains(Args& a, int sms, bool flips, cudaStream_t s) {
+    const int smem = (int)smem_bytes(a.t);
     RNNWF_CHECK(smem <= kSmemLimit, -3, "tensor-core chain kernel needs %d bytes of shared memory", smem);
-    prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, t, params, img);
     {
-        RNNWF_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
-        auto k = chain_kernel<50, true>;
+        RNNWF_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), s));
+        auto k = chain_kernel<50, true, CPLX>;
         RNNWF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         prof_count();
         k<<<std::min(a.tiles128, sms), kThreads, smem, s>>>(a);
         RNNWF_CUDA(cudaGetLastError());
     }
     if (flips) {
-        RNNWF_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
-        auto k = chain_kernel<50, false>;
+        RNNWF_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), s));
+        auto k = chain_kernel<50, false, CPLX>;
         RNNWF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        const int grid = (int)std::min<int64_t>((int64_t)g.N * a.tiles128, sms);
+        const int grid = (int)std::min<int64_t>((int64_t)a.nslots * a.tiles128, sms);
         prof_count();
         prof_mark(0, s);
         k<<<grid, kThreads, smem, s>>>(a);
@@ -499,6 +542,43 @@ static int launch_eloc(const GruLayout& g, int Mold, int tiles, const float* par
         RNNWF_CUDA(cudaGetLastError());
     }
     return 0;
+}
+
+static Args make_args(const GruLayout& g, int Mold, int tiles, unsigned char* img, const uint8_t* sigT, float* hstore, double* la_sel,
+                      double* la_oth, double* lp, double* delta, int* counter, int& sms) {
+    int dev = 0;
+    sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    Args a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.t = make_layout(g); a.Mold = Mold;
+    a.rows_total = (int64_t)tiles * Mold;
+    a.tiles128 = (int)cdiv(a.rows_total, kRows);
+    a.img = img; a.sigT = sigT; a.hstore = hstore; a.la_sel = la_sel; a.la_oth = la_oth; a.lp = lp; a.delta = delta; a.counter = counter;
+    a.nslots = g.N;
+    return a;
+}
+
+// base pass + single-flip chains (replaces launch_forward<STASH> + launch_chain for the FP32 pRNN with 50 units)
+static int launch_eloc(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
+                       double* la_sel, double* la_oth, double* lp, double* delta, int* counter, bool flips, cudaStream_t s) {
+    int sms;
+    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, lp, delta, counter, sms);
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);
+    return launch_chains<false>(a, sms, flips, s);
+}
+
+// base pass + NN / NNN exchange chains of the complex cRNN (J1-J2); `order` lists the 2N-3 slots by decreasing chain length
+static int launch_j1j2(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
+                       double* la_sel, double* la_oth, double* ph_sel, double* ph_oth, double* lp_re, double* lp_im, double* delta_re,
+                       double* delta_im, const int* order, const double* j1, const double* j2, int* counter, cudaStream_t s) {
+    int sms;
+    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, lp_re, delta_re, counter, sms);
+    a.ph_sel = ph_sel; a.ph_oth = ph_oth; a.lp_im = lp_im; a.delta_im = delta_im; a.order = order; a.j1 = j1; a.j2 = j2;
+    a.n_kind1 = g.N - 1; a.n_kind2 = g.N - 2; a.nslots = a.n_kind1 + a.n_kind2;
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);
+    return launch_chains<true>(a, sms, true, s);
 }
 
 }  // namespace tc16

@@ -127,12 +127,25 @@ int gru_j1j2_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     const int nslots = 2 * g.N;
     Ws ws(wsp, wsb);
     GruWs<T> w = carve_gru<T>(ws, g, c, tiles, true, nslots, true, ns);
+    ws.take<float>((size_t)ns * (2 * g.N + 1));                         // (kept for layout compatibility with rnnwf_workspace_bytes)
+    unsigned char* img16 = nullptr;
+    if (std::is_same<T, float>::value && tc16::supported(g)) img16 = ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
     prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles, 1);
-    if (int e = launch_forward<T, true, true>(g, c, w, tiles, s)) return e;
     ChainPlan plan{g.N - 1 + g.N - 2, 0, g.N - 1, g.N - 2, tiles, j1, j2};
-    if (int e = launch_chain<T, true>(g, c, plan, w, s)) return e;
+    const char* env = getenv("RNNWF_CHAIN");
+    if (img16 && !(env && strcmp(env, "ffma") == 0)) {   // tcgen05 3xFP16 kernel (gru_tc16.cuh)
+        if constexpr (std::is_same<T, float>::value) {
+            prof_count(); chain_order_kernel<<<1, 1, 0, s>>>(plan, w.order);
+            if (int e = tc16::launch_j1j2(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth,
+                                          w.lp_re, w.lp_im, w.delta_re, w.delta_im, w.order, j1, j2, w.counter, s))
+                return e;
+        }
+    } else {
+        if (int e = launch_forward<T, true, true>(g, c, w, tiles, s)) return e;
+        if (int e = launch_chain<T, true>(g, c, plan, w, s)) return e;
+    }
     prof_count(); j1j2_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, c.M, j1, j2, bz, marshall, w.delta_re, w.delta_im,
                                                                            w.lp_re, w.lp_im, plan.nslots, eloc, logpsi);
     RNNWF_CUDA(cudaGetLastError());

@@ -51,3 +51,32 @@ def test_tc_chain_matches_ffma_and_oracle(L, N, ns, parity, chain):
         lpf = (lambda c: O.log_probability_parity(p, c)) if parity else (lambda c: O.log_probability(p, c))
         ref = O.ising_local_energies(Jz, 0.9, s, lpf)
         np.testing.assert_allclose(e_tc, ref, rtol=1e-5)
+
+
+@pytest.mark.parametrize("L,N,ns,marshall,j2", [(1, 12, 150, False, 0.2), (2, 16, 260, True, 0.5), (1, 10, 40, True, 0.0)])
+def test_tc_j1j2_exchange_chains_match_ffma_and_oracle(L, N, ns, marshall, j2):
+    heads = ("wf_dense_ampl", "wf_dense_phase")
+    units = [50] * L
+    p = O.randomize_biases(O.init_gru_params(units, seed=L + 3, dtype=np.float32, heads=heads, scale=1.5), seed=L + 4)
+    model = ops.make_model(head=ops.HEAD_COMPLEX, num_layers=L, units=50, n_sites=N)
+    flat = torch.tensor(O.flatten(p), device=dev())
+    s = O.crnn_sample(p, ns, N, seed=3)
+    rng = np.random.default_rng(4)
+    J1, J2, Bz = rng.uniform(0.5, 1.5, N), j2 * np.ones(N), rng.uniform(-0.2, 0.2, N)
+    if j2:
+        J2[2] = 0.0
+    out = {}
+    for chain in ("tc16", "ffma"):
+        os.environ["RNNWF_CHAIN"] = chain
+        try:
+            e, la = ops.j1j2_eloc(model, flat, u8(s), J1, J2, Bz, marshall_sign=marshall)
+            out[chain] = (e.cpu().numpy(), la.cpu().numpy())
+        finally:
+            os.environ.pop("RNNWF_CHAIN", None)
+    ref = O.j1j2_local_energies(J1, J2, Bz, s, lambda c: O.crnn_log_amplitude(p, c), marshall_sign=marshall)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(out["tc16"][0] - out["ffma"][0]).max() < 2e-5 * scale
+    assert np.abs(out["tc16"][0] - ref).max() < 3e-5 * scale                 # the reference combine is complex64
+    la_ref = O.crnn_log_amplitude(p, s)
+    np.testing.assert_allclose(out["tc16"][1].real, la_ref.real, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out["tc16"][1].imag, la_ref.imag, rtol=1e-5, atol=2e-5)
