@@ -290,8 +290,12 @@ def run_b200_arm(args):
                         peak_kind=("dense 16-bit tensor peak, sustained figure of MEASURED_PEAKS.json (kernel timed inside a multi-second step)"
                                    if peaks else "fallback: 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)") +
                                   ("" if mode == 2 else "; kind::tf32 runs at half the 16-bit rate"),
+                        peak_over_passes=peak / 3.0, frac_of_peak_over_passes=achieved / (peak / 3.0),
+                        tf32x3_roofline=(peak / 2.0 if mode == 2 else peak) / 3.0,
                         tensor_pipe_tflops_executed=executed / (chain_ms * 1e-3) / 1e12,
                         tensor_pipe_frac_executed=executed / (chain_ms * 1e-3) / 1e12 / peak,
+                        note_rooflines="peak_over_passes = tensor peak / 3: the ceiling of any 3-pass split-operand scheme with FP32-grade accuracy on "
+                                       "this pipe; tf32x3_roofline = (16-bit peak / 2) / 3: the ceiling of the 3xTF32 scheme BASELINE.json's north_star names",
                         note="achieved counts ALGORITHMIC flops (75 800 per GRU-stack evaluation); FP32-grade accuracy costs 3 tensor passes "
                              "over padded 160-column tiles, so the tensor pipe executes ~3.6x the algorithmic flops; the per-site dependency "
                              "chain (MMA -> gate math -> operand restaging) serialises the rest")

@@ -12,7 +12,7 @@ is not installable here.  What *is* pinned:
   * GRU structure: parameter counts 422 / 444 (Tutorial_1DTFIM.ipynb#cell15, Tutorial_1DJ1J2.ipynb#cell15);
   * physics: exact diagonalisation / free-fermion energies (Tutorial_1DTFIM.ipynb#cell8, #cell24).
 The floating-point RNN arithmetic itself is "parity unpinned" against TF1.13 (no TF run available);
-it is cross-checked against `torch.nn.GRUCell` (same equations) and the C restatement in oracle/gru_ref.c.
+it is cross-checked against `torch.nn.GRUCell` (same equations, tests/test_oracle.py).
 
 All `file:line` citations are relative to /root/reference.
 """
