@@ -276,7 +276,12 @@ def run_b200_arm(args):
         # executed tensor-pipe flops: 3 operand passes, padded tiles: per (site, 128-row tile, layer) MMAs of
         # 2*128*N*K flops each
         tiles128 = -(-(ndir * (-(-ns // 120)) * 120) // 128)
-        if mode == 2:
+        if mode == 3:
+            per_l0 = 2 * 128 * 16 * (2 * 112 + 12 * 112 + 2 * 64 + 12 * 64)
+            per_l1 = 2 * 128 * 16 * (24 * 112 + 24 * 64)
+            kname = ("tc16p::chain_kernel<false,false> (tcgen05 kind::f16, 3xFP16 operands, weights resident in shared memory, MMA and gate "
+                     "math software-pipelined over anti-diagonals of the (site, layer) grid)")
+        elif mode == 2:
             per_l0 = 2 * 128 * 16 * (2 * 160 + 64 + 12 * 160)
             per_l1 = 2 * 128 * 16 * (12 * 160 + 64 + 12 * 160)
             kname = "tc16::chain_kernel<50,false> (tcgen05 kind::f16, 3xFP16 operands, weights resident in shared memory)"
@@ -285,20 +290,21 @@ def run_b200_arm(args):
             per_l1 = 2 * 128 * 8 * (21 * 192 + 21 * (128 + 64))
             kname = "gru_chain_tc_kernel<50,false> (tcgen05 kind::tf32, 3xTF32 operands)"
         executed = tiles128 * (N * (N - 1) / 2.0) * (per_l0 + (LAYERS - 1) * per_l1)
-        peak = float(peaks.get("bf16_tflops_sustained", 1399.0)) / (1.0 if mode == 2 else 2.0)
+        peak = float(peaks.get("bf16_tflops_sustained", 1399.0)) / (1.0 if mode >= 2 else 2.0)
         roofline = dict(common, bound="tensor", kernel=kname, peak=peak, frac=achieved / peak,
                         peak_kind=("dense 16-bit tensor peak, sustained figure of MEASURED_PEAKS.json (kernel timed inside a multi-second step)"
                                    if peaks else "fallback: 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)") +
-                                  ("" if mode == 2 else "; kind::tf32 runs at half the 16-bit rate"),
+                                  ("" if mode >= 2 else "; kind::tf32 runs at half the 16-bit rate"),
                         peak_over_passes=peak / 3.0, frac_of_peak_over_passes=achieved / (peak / 3.0),
-                        tf32x3_roofline=(peak / 2.0 if mode == 2 else peak) / 3.0,
+                        tf32x3_roofline=(peak / 2.0 if mode >= 2 else peak) / 3.0,
                         tensor_pipe_tflops_executed=executed / (chain_ms * 1e-3) / 1e12,
                         tensor_pipe_frac_executed=executed / (chain_ms * 1e-3) / 1e12 / peak,
                         note_rooflines="peak_over_passes = tensor peak / 3: the ceiling of any 3-pass split-operand scheme with FP32-grade accuracy on "
                                        "this pipe; tf32x3_roofline = (16-bit peak / 2) / 3: the ceiling of the 3xTF32 scheme BASELINE.json's north_star names",
                         note="achieved counts ALGORITHMIC flops (75 800 per GRU-stack evaluation); FP32-grade accuracy costs 3 tensor passes "
-                             "over padded 160-column tiles, so the tensor pipe executes ~3.6x the algorithmic flops; the per-site dependency "
-                             "chain (MMA -> gate math -> operand restaging) serialises the rest")
+                             "over padded tiles (K 51 -> 64, N 150 -> 176/160), so the tensor pipe executes ~3.6-4x the algorithmic flops; every "
+                             "instruction with a new A chunk pays ~81 cycles of TMEM operand fetch whatever its N (measured, scripts/mma_probe2.py), "
+                             "and the recurrence leaves one (site, layer) step of look-ahead")
 
     # ---- end to end through the reference-facing host API (host buffers, copies inside the timed region) ----
     e2e = None

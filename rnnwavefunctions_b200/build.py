@@ -53,7 +53,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         obj = os.path.join(BUILD, os.path.basename(src)[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_mtime):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("RNNWF_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]   # e.g. -DRNNWF_TC16P_DEBUG
         if verbose:
             print("[rnnwf build]", " ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -255,17 +255,24 @@ static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, ui
 }  // namespace rnnwf
 #include "gru_tc.cuh"
 #include "gru_tc16.cuh"
+#include "gru_tc16p.cuh"
 namespace rnnwf {
 
 // Chain-kernel selection for the FP32 probability-head pRNN (A/B measurements through RNNWF_CHAIN):
-//   default / "tc16": tcgen05 kind::f16, 3xFP16 operands, all weights resident (gru_tc16.cuh)
+//   default / "tc16p": tcgen05 kind::f16, 3xFP16 operands, all weights resident, MMA / gate math software-pipelined over
+//                      anti-diagonals of the (site, layer) grid (gru_tc16p.cuh)
+//   "tc16"          : the same arithmetic with MMA and gate math alternating (gru_tc16.cuh)
 //   "tc32"          : tcgen05 kind::tf32, 3xTF32 operands, site-blocked weight swapping (gru_tc.cuh)
 //   "ffma"          : CUDA-core tile engine (gru_chain_kernel; the path every other shape / dtype takes)
+static size_t tc16_img_bytes(const GruLayout& g) {   // one image buffer serves either 3xFP16 kernel generation
+    return std::max<size_t>(tc16::make_layout(g).img_bytes, tc16p::make_layout(g).img_bytes);
+}
 static int chain_mode(const GruLayout& g) {
     const char* e = getenv("RNNWF_CHAIN");
     if (e && strcmp(e, "ffma") == 0) return 0;
     if (e && strcmp(e, "tc32") == 0) return tc_supported(g) ? 1 : 0;
-    return tc16::supported(g) ? 2 : (tc_supported(g) ? 1 : 0);
+    if (e && strcmp(e, "tc16") == 0) return tc16::supported(g) ? 2 : 0;
+    return tc16p::supported(g) ? 3 : (tc16::supported(g) ? 2 : (tc_supported(g) ? 1 : 0));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,12 +293,12 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
         case RNNWF_OP_TFIM_ELOC:
             carve_gru<T>(ws, g, c, tiles, true, g.N, cplx, ns);
             if (std::is_same<T, float>::value && tc_supported(g)) carve_tc(ws, g, make_tc_layout(g), 160);
-            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
+            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16_img_bytes(g));
             break;
         case RNNWF_OP_J1J2_ELOC:
             carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns);
             ws.take<float>((size_t)ns * (2 * g.N + 1));
-            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
+            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16_img_bytes(g));
             break;
         case RNNWF_OP_VMC_GRAD: return gru_grad_workspace_bytes<T>(m, ns, flags);
         default: return 0;
@@ -362,13 +369,19 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     const bool tc = std::is_same<T, float>::value && tc_supported(g);
     if (tc) tw = carve_tc(ws, g, make_tc_layout(g), 160);
     unsigned char* img16 = nullptr;
-    if (std::is_same<T, float>::value && tc16::supported(g)) img16 = ws.take<unsigned char>(tc16::make_layout(g).img_bytes);
+    if (std::is_same<T, float>::value && tc16::supported(g)) img16 = ws.take<unsigned char>(tc16_img_bytes(g));
     const int mode = std::is_same<T, float>::value ? chain_mode(g) : 0;
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
     prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
     prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
-    if (mode == 2) {
+    if (mode == 3) {
+        if constexpr (std::is_same<T, float>::value) {
+            if (int e = tc16p::launch_eloc(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.lp_re, w.delta_re,
+                                           w.counter, bx != 0.0, s))
+                return e;
+        }
+    } else if (mode == 2) {
         if constexpr (std::is_same<T, float>::value) {
             if (int e = tc16::launch_eloc(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.lp_re, w.delta_re,
                                           w.counter, bx != 0.0, s))

@@ -1,0 +1,744 @@
+// gru_tc16p.cuh — tensor-core chain kernel, generation 3: the tcgen05 3xFP16 recurrence of gru_tc16.cuh, software-pipelined so
+// that the tensor pipe and the gate math (MUFU / FMA pipes) run concurrently instead of alternating, with a hot loop small
+// enough for the SM's instruction cache.
+//
+// Same contract as tc16::chain_kernel (TFIM single flips 1DTFIM/TrainingRNN_1DTFIM.py:43-48,74; J1-J2 exchanges
+// J1J2/TrainingRNN_J1J2.py:68-92; base pass = teacher-forced log-probability 1DTFIM/RNNwavefunction.py:76-118).
+//
+// What changed against generation 2 (which serialises MMA -> gate math -> operand restaging per (site, layer) because TMEM has
+// no room for a second accumulator set):
+//   * the accumulators of one (site, layer) step are split by gate into D_ru = [r | u] and D_c = [cx] [ch], written by two
+//     MMA groups M_ru / M_c with their own commit barriers.  The row warps run G_ru (reset / update gates from D_ru) while the
+//     tensor pipe is still busy with M_c, then G_c (candidate, new state, restaging).
+//   * the (site, layer) steps of a chain are visited along anti-diagonals of the (site, layer) grid, top layer first:
+//     ..., (n-2, 2), (n-1, 1), (n, 0), (n-1, 2), (n, 1), (n+1, 0), ...  With three layers no step consumes the output of the
+//     step right before it, so M_ru of step k+1 is issued as soon as G_ru of step k has drained D_ru and runs under G_c of
+//     step k; M_c of step k+1 runs under G_ru of step k+1.  (With fewer layers the dependent steps wait for the restaged
+//     state; M_c still overlaps G_ru.)
+//   * all row-warp <-> MMA-warp hand-offs are mbarriers (no CTA-wide bar.sync in the site loop).
+//   * ONE copy of the step code serves both unit halves of a row and every layer (measured: with the fully specialised
+//     150 KB loop body of the first version the SMs of a GPC ran at the speed of their shared instruction fetch path — the
+//     first TPC of each GPC at 4 500 cycles per step, the others at 6 500 - 10 000).  The two row threads of a sample own 25
+//     units each, placed at aligned TMEM columns so that the same instructions work for either half with a runtime offset;
+//     the per-layer hidden-state registers are rotated with moves instead of unrolling the layer loop.
+// TMEM columns: D_r [0,56) D_u [56,112) | D_cx [112,176) | D_ch [176,240) | R_l (h^l: 32 hi + 32 lo packed half pairs) at 240 + 64 l |
+//               X0 (one-hot input of layer 0) at 240 + 64 L.
+//   gate block (56 columns): unit j < 25 at column j, unit j >= 25 at column j + 3 (second half starts at 28)
+//   operand region (K = 64):  unit j < 25 at k = j, the constant 1 (bias column) at k = 25, unit j >= 25 at k = j + 7 (32..56)
+// Shared memory: per layer the K-major core-matrix images HRU_hi | HRU_lo | HC_hi | HC_lo | XRU_hi | XRU_lo | XC_hi | XC_lo
+// (RU: 112 rows = [r(56) | u(56)], C: 56 rows; the N = 64 candidate MMAs run 8 rows into whatever follows — those rows only
+// produce accumulator columns nobody reads).
+// Included by gru.cu.
+#pragma once
+#include "gru_tc16.cuh"
+
+namespace rnnwf {
+namespace tc16p {
+
+using tc16::ex2;
+using tc16::rcp;
+using tc16::pack_h2;
+using tc16::unpack_h2;
+using tc16::core_off;
+
+constexpr int kRows = 128, kRowThreads = 256, kThreads = 288, kMmaWarp = 8;
+constexpr int kUP = 25;                                  // units per row thread (H = 50, two threads per row)
+constexpr int kBW = 56;                                  // accumulator columns per gate block
+constexpr int kNRU = 112, kNC = 64;                      // N of the M_ru / M_c instructions
+constexpr int kRowsRU = 112, kRowsC = 56;                // stored B rows of the [r | u] and candidate images
+constexpr int kKp = 64, kKC = 8;                         // K padded to 4 MMA steps of 16; 16-byte chunks per row
+constexpr int kColRU = 0, kColCX = 112, kColCH = 176, kColR = 240;
+constexpr int kKOne = kUP;                               // K index of the constant-1 (bias) column
+enum { kFullRU = 0, kFullC = 1, kRuFree = 2, kCDone = 3, kWImg = 4, kNumBars = 5 };
+
+__host__ __device__ __forceinline__ int unit_of_col(int c) { return c < kUP ? c : (c >= 28 && c < 28 + kUP ? c - 3 : -1); }   // gate-block column -> unit
+__host__ __device__ __forceinline__ int unit_of_k(int k) { return k < kUP ? k : (k >= 32 && k < 32 + kUP ? k - 7 : -1); }     // operand K index -> unit
+
+struct Layout {
+    int L, H, N;
+    int ru_bytes, c_bytes, ru0_bytes, c0_bytes;   // one precision half of an [r|u] / candidate image with K = 64 / K = 16 (layer 0 input)
+    int l0_bytes, l1_bytes;
+    int tab_off, tab_floats, img_bytes;
+};
+
+inline Layout make_layout(const GruLayout& g) {
+    Layout t;
+    t.L = g.L; t.H = g.H; t.N = g.N;
+    t.ru_bytes = kRowsRU * kKp * 2;
+    t.c_bytes = kRowsC * kKp * 2;
+    t.ru0_bytes = kRowsRU * 16 * 2;
+    t.c0_bytes = kRowsC * 16 * 2;
+    t.l0_bytes = 2 * (t.ru_bytes + t.c_bytes) + 2 * (t.ru0_bytes + t.c0_bytes);
+    t.l1_bytes = 4 * (t.ru_bytes + t.c_bytes);
+    t.tab_off = t.l0_bytes + (g.L - 1) * t.l1_bytes;
+    t.tab_floats = g.nheads * (2 * 64 + 4);       // per head: Wd[64][2] | bd[2] | pad
+    t.img_bytes = t.tab_off + t.tab_floats * 4;
+    return t;
+}
+
+inline size_t smem_bytes(const Layout& t) {
+    // image | head partial sums [2][128] float4 | barriers | tmem slot | work slot (the candidate MMAs over-read <= 1 KB past the images)
+    return (size_t)((t.img_bytes + 15) & ~15) + (size_t)2 * kRows * sizeof(float4) + 128;
+}
+
+inline bool supported(const GruLayout& g) {
+    if (!(g.H == 50 && g.N >= 2 && g.L >= 1 && g.L <= 3)) return false;
+    return smem_bytes(make_layout(g)) <= (size_t)kSmemLimit;
+}
+
+// flat TF-order parameters -> shared-memory image.  Weights are pre-scaled so that the gates are 1/(1 + 2^a): r, u rows by
+// -log2(e), candidate rows by 2 log2(e); the constant-1 K column carries the biases bg (h part of r, u), bch (h part of the
+// candidate) and bci (x part of the candidate).  Layer 0: the x images have K = 16 with the two one-hot rows of the input kernels
+// at k = 0, 1 and bci at k = 2.
+__global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ flat, unsigned char* __restrict__ img) {
+    const int H = g.H;
+    const float kS = -1.4426950408889634f, kC = 2.8853900817779268f;
+    constexpr int kRowsAll = kRowsRU + kRowsC;          // 168 stored rows per (layer, part)
+    const int per_l = 2 * kRowsAll * kKp;               // h part + x part
+    const int total = g.L * per_l;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int l = idx / per_l;
+        int q = idx % per_l;
+        const int xpart = q / (kRowsAll * kKp);
+        q %= kRowsAll * kKp;
+        const int n = q / kKp, k = q % kKp;
+        const int d = g.d[l];
+        const float* Kg = flat + g.flat_off[l];
+        const float* bg = Kg + (d + H) * 2 * H;
+        const float* Kci = bg + 2 * H;
+        const float* Kch = Kci + d * H;
+        const float* bci = Kch + H * H;
+        const float* bch = bci + H;
+        unsigned char* Lb = img + (l == 0 ? 0 : t.l0_bytes + (l - 1) * t.l1_bytes);
+        const bool ru = n < kRowsRU;
+        const int gate = ru ? n / kBW : 0;
+        const int j = unit_of_col(ru ? n % kBW : n - kRowsRU);   // output unit of this row (-1: padding)
+        const int nn = ru ? n : n - kRowsRU;                     // row inside its image
+        const int ku = unit_of_k(k);                             // input unit of this K index (-1: constant / padding)
+        float v = 0.f;
+        int KC = kKC;
+        unsigned char *hi_b, *lo_b;
+        if (!xpart) {
+            if (j >= 0) {
+                if (ru) v = ku >= 0 ? kS * Kg[(d + ku) * 2 * H + gate * H + j] : (k == kKOne ? kS * bg[gate * H + j] : 0.f);
+                else v = ku >= 0 ? kC * Kch[ku * H + j] : (k == kKOne ? kC * bch[j] : 0.f);
+            }
+            hi_b = Lb + (ru ? 0 : 2 * t.ru_bytes);
+            lo_b = hi_b + (ru ? t.ru_bytes : t.c_bytes);
+        } else {
+            unsigned char* Xb = Lb + 2 * (t.ru_bytes + t.c_bytes);
+            if (l > 0) {
+                if (j >= 0) {
+                    if (ru) v = ku >= 0 ? kS * Kg[ku * 2 * H + gate * H + j] : 0.f;
+                    else v = ku >= 0 ? kC * Kci[ku * H + j] : (k == kKOne ? kC * bci[j] : 0.f);
+                }
+                hi_b = Xb + (ru ? 0 : 2 * t.ru_bytes);
+                lo_b = hi_b + (ru ? t.ru_bytes : t.c_bytes);
+            } else {
+                if (k >= 16) continue;
+                KC = 2;
+                if (j >= 0) {
+                    if (ru) v = k < 2 ? kS * Kg[k * 2 * H + gate * H + j] : 0.f;
+                    else v = k < 2 ? kC * Kci[k * H + j] : (k == 2 ? kC * bci[j] : 0.f);
+                }
+                hi_b = Xb + (ru ? 0 : 2 * t.ru0_bytes);
+                lo_b = hi_b + (ru ? t.ru0_bytes : t.c0_bytes);
+            }
+        }
+        const __half hi = __float2half_rn(v);
+        reinterpret_cast<__half*>(hi_b)[core_off(nn, k, KC)] = hi;
+        reinterpret_cast<__half*>(lo_b)[core_off(nn, k, KC)] = __float2half_rn(v - __half2float(hi));
+    }
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < t.tab_floats; idx += gridDim.x * blockDim.x) {
+        const int hd = idx / 132, r = idx % 132;        // per head: Wd[j][2] (64 x 2) | bd[2] | pad
+        const float* hw = flat + g.flat_head + hd * (2 * H + 2);
+        float v = 0.f;
+        if (r < 128) { if (r / 2 < H) v = hw[r]; }
+        else if (r < 130) v = hw[2 * H + (r - 128)];
+        reinterpret_cast<float*>(img + t.tab_off)[idx] = v;
+    }
+}
+
+// (hi, lo) FP16 pairs of 2 * NC consecutive values -> NC operand-region columns (two values per column)
+template <int NC> __device__ __forceinline__ void stage_cols(uint32_t col, const float* h) {
+    float hi[NC], lo[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        const uint32_t wh = pack_h2(h[2 * c], h[2 * c + 1]);
+        const float2 f = unpack_h2(wh);
+        hi[c] = __uint_as_float(wh);
+        lo[c] = __uint_as_float(pack_h2(h[2 * c] - f.x, h[2 * c + 1] - f.y));
+    }
+    if constexpr (NC == 4) {
+        umma::tmem_st4(col, hi);
+        umma::tmem_st4(col + 32, lo);
+    } else {
+        static_assert(NC == 1, "column groups are 4 wide or the single tail column");
+        umma::tmem_st1(col, hi);
+        umma::tmem_st1(col + 32, lo);
+    }
+}
+// the 25 units of a row thread (+ its half of the constant-1 column) -> columns [16 part, 16 part + 13) of an operand region
+__device__ __forceinline__ void stage_all(uint32_t reg_part_addr, const float* hp, float one) {
+#pragma unroll
+    for (int gq = 0; gq < 3; ++gq) stage_cols<4>(reg_part_addr + 4 * gq, hp + 8 * gq);
+    const float tail[2] = {hp[24], one};
+    stage_cols<1>(reg_part_addr + 12, tail);
+}
+
+struct Args {
+    GruLayout g;
+    Layout t;
+    int Mold, tiles128;
+    int64_t rows_total;
+    const unsigned char* img;
+    const uint8_t* sigT;
+    float* hstore;            // BASE: written (every layer, every site); FLIP: restart states
+    double *la_sel, *la_oth;  // BASE: written; FLIP: read
+    double* lp;               // BASE: sum_n la_sel
+    double* delta;            // FLIP: [tile][slot][M]
+    int* counter;
+    // complex cRNN / J1-J2 exchanges (CPLX instantiations): phases, imaginary parts, slot plan
+    double *ph_sel, *ph_oth, *lp_im, *delta_im;
+    const int* order;         // slots by decreasing chain length
+    const double *j1, *j2;    // couplings: slots with a zero coupling are skipped (J1J2/TrainingRNN_J1J2.py:69,84)
+    int n_kind1, n_kind2, nslots;
+};
+
+// per-row-thread state of one chain
+struct Ctx {
+    const float* tab;
+    float4* zsm;
+    uint64_t* bars;
+    uint32_t lane_addr;
+    int rowi, m, part;
+    bool live;
+    size_t rowbase;
+    int s, t;                 // modified sites (s = -1: none)
+    uint32_t g, cda;          // steps done by this CTA so far (phase index of full_ru / full_c / ru_free); next c_done phase index
+    float4 pz;                // pending head (part 0): partial sums, selected outcome, site, c_done phase and zsm buffer of that step
+    int psg, pn;
+    uint32_t pph, pbuf;
+    double p_la, p_ph;        // base-pass la_sel / ph_sel of the pending site (loaded a step ahead: global latency off the critical path)
+    int nup;
+    double acc, acc_im;
+#ifdef RNNWF_TC16P_DEBUG
+    long long w_ru, w_c, t_ru, t_c;   // cycles: waiting for full_ru / full_c, inside G_ru / G_c
+#endif
+};
+#ifdef RNNWF_TC16P_DEBUG
+#define TCP_T(...) __VA_ARGS__
+#else
+#define TCP_T(...)
+#endif
+
+template <bool BASE> __device__ __forceinline__ int spin_of(const Args& a, const Ctx& c, int q) {
+    int v = a.sigT[(c.rowbase + q) * a.Mold + c.m];
+    if (!BASE && (q == c.s || q == c.t)) v = 1 - v;
+    return v;
+}
+
+// log-softmax / amplitude / phase of the pending top-layer step (part 0 only); part 1's partial sums come through zsm
+template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(const Args& a, Ctx& c) {
+    if (c.pn < 0) return;
+    const int pn = c.pn, psg = c.psg, N = a.g.N;
+    c.pn = -1;
+    umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
+    if (!c.live) return;
+    float4 pz = c.pz;
+    {
+        const float4 o = c.zsm[c.pbuf * kRows + c.rowi];
+        pz.x += o.x; pz.y += o.y; pz.z += o.z; pz.w += o.w;
+    }
+    const float* tab = c.tab;
+    const float f0 = pz.x + tab[128], f1 = pz.y + tab[129];
+    // log softmax of the 2-way head in FP32 (log1pf/expf, ~1e-7 relative); the site terms are summed in FP64
+    const float dsel = psg ? f0 - f1 : f1 - f0;                             // z_other - z_selected
+    double ls = dsel > 30.f ? -(double)dsel : -(double)log1pf(expf(dsel));
+    double lo = -dsel > 30.f ? (double)dsel : -(double)log1pf(expf(-dsel));
+    double ps = 0.0, po = 0.0;
+    if (CPLX) {
+        // amplitude = sqrt(softmax) with the zero-magnetisation mask and renormalisation
+        // (J1J2/ComplexRNNwavefunction.py:85-93,147-155); phase = pi * softsign (:8-9)
+        ls *= 0.5;
+        lo *= 0.5;
+        if (2 * pn >= N) {
+            const int half = N / 2, ndn = pn - c.nup;
+            const bool ok_dn = (half - 1 - ndn) >= 0, ok_up = (half - 1 - c.nup) >= 0;
+            const bool ok_sel = psg ? ok_up : ok_dn, ok_oth = psg ? ok_dn : ok_up;
+            const double ninf = -__longlong_as_double(0x7ff0000000000000LL);
+            if (!ok_sel) ls = ninf; else if (!ok_oth) ls = 0.0;
+            if (!ok_oth) lo = ninf; else if (!ok_sel) lo = 0.0;
+        }
+        const float y0 = pz.z + tab[132 + 128], y1 = pz.w + tab[132 + 129];
+        const double ys = psg ? (double)y1 : (double)y0, yo = psg ? (double)y0 : (double)y1;
+        ps = kPi * ys / (1.0 + fabs(ys));
+        po = kPi * yo / (1.0 + fabs(yo));
+        c.nup += psg;
+    }
+    const size_t o_ = (c.rowbase + pn) * a.Mold + c.m;
+    if (BASE) {
+        a.la_sel[o_] = ls;
+        a.la_oth[o_] = lo;
+        c.acc += ls;
+        if (CPLX) { a.ph_sel[o_] = ps; a.ph_oth[o_] = po; c.acc_im += ps; }
+    } else {
+        c.acc += ls - c.p_la;
+        if (CPLX) c.acc_im += ps - c.p_ph;
+    }
+}
+
+// one (site n, layer l) step of a row thread: G_ru on D_ru, then G_c on D_cx / D_ch + restaging of the new state.
+// hp: this thread's 25 units of h^l (previous site in, this site out).
+template <bool BASE, bool CPLX>
+__device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, float* hp) {
+    constexpr int H = 50;
+    const int L = a.g.L, N = a.g.N, Mold = a.Mold, part = c.part;
+    const bool top = l == L - 1;
+    const uint32_t par = c.g & 1;
+    const uint32_t dpart = c.lane_addr + 28 * part;                       // this thread's columns inside a gate block
+    // global loads this step will need at its end are issued before the first wait (part 0): the spin of site n (one-hot input of
+    // (n + 1, 0) / selected outcome of the head) and the base-pass terms of site n
+    int spin_n = 0;
+    double la_n = 0.0, ph_n = 0.0;
+    if (part == 0 && c.live && (l == 0 || top)) {
+        spin_n = spin_of<BASE>(a, c, n);
+        if (!BASE && top) {
+            la_n = a.la_sel[(c.rowbase + n) * Mold + c.m];
+            if (CPLX) ph_n = a.ph_sel[(c.rowbase + n) * Mold + c.m];
+        }
+    }
+    // ---- G_ru: reset / update gates.  Two units at a time: 1/(1+2^a) for r0, u0, r1, u1 share ONE reciprocal (exponents
+    // clamped to 30, so the product of the four denominators stays below 2^121)
+    TCP_T(long long t0 = clock64();)
+    umma::mbar_wait(&c.bars[kFullRU], par);
+    umma::fence_after_sync();
+    TCP_T(long long t1 = clock64(); c.w_ru += t1 - t0;)
+    float rr[kUP], uu[kUP];
+#pragma unroll
+    for (int gq = 0; gq < 3; ++gq) {
+        umma::tmem_ld8p(dpart + kColRU + 8 * gq, rr + 8 * gq);
+        umma::tmem_ld8p(dpart + kColRU + kBW + 8 * gq, uu + 8 * gq);
+    }
+    umma::tmem_ld1p(dpart + kColRU + 24, rr + 24);
+    umma::tmem_ld1p(dpart + kColRU + kBW + 24, uu + 24);
+    umma::wait_ld();
+    umma::fence_before_sync();
+    umma::mbar_arrive(&c.bars[kRuFree]);               // D_ru may be overwritten by the next step's M_ru
+#pragma unroll
+    for (int q = 0; q < kUP - 1; q += 2) {
+        const float er0 = 1.0f + ex2(fminf(rr[q], 30.f)), eu0 = 1.0f + ex2(fminf(uu[q], 30.f));
+        const float er1 = 1.0f + ex2(fminf(rr[q + 1], 30.f)), eu1 = 1.0f + ex2(fminf(uu[q + 1], 30.f));
+        const float p0 = er0 * eu0, p1 = er1 * eu1;
+        const float inv = rcp(p0 * p1);
+        const float i0 = inv * p1, i1 = inv * p0;                          // 1/p0, 1/p1
+        rr[q] = i0 * eu0; uu[q] = i0 * er0;
+        rr[q + 1] = i1 * eu1; uu[q + 1] = i1 * er1;
+    }
+    {
+        const float er = 1.0f + ex2(fminf(rr[kUP - 1], 30.f)), eu = 1.0f + ex2(fminf(uu[kUP - 1], 30.f));
+        const float inv = rcp(er * eu);
+        rr[kUP - 1] = inv * eu; uu[kUP - 1] = inv * er;
+    }
+    // ---- G_c: candidate, new state, head partial sums, restaging
+    TCP_T(long long t2 = clock64(); c.t_ru += t2 - t1;)
+    umma::mbar_wait(&c.bars[kFullC], par);
+    umma::fence_after_sync();
+    TCP_T(long long t3 = clock64(); c.w_c += t3 - t2;)
+    if (part == 0) finish_head<BASE, CPLX>(a, c);
+    const uint32_t reg = c.lane_addr + kColR + 64 * l + 16 * part;
+    const float* tab = c.tab + 2 * kUP * part;
+    float* hst = BASE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kUP * part) * Mold + c.m : nullptr;
+    float z0 = 0.f, z1 = 0.f, y0 = 0.f, y1 = 0.f;
+#pragma unroll
+    for (int gq = 0; gq < 3; ++gq) {
+        float dc[8], dq[8];
+        umma::tmem_ld8p(dpart + kColCX + 8 * gq, dc);
+        umma::tmem_ld8p(dpart + kColCH + 8 * gq, dq);
+        umma::wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+            const int jl = 8 * gq + q;
+            const float ec0 = 1.0f + ex2(fminf(fmaf(rr[jl], dq[q], dc[q]), 60.f));
+            const float ec1 = 1.0f + ex2(fminf(fmaf(rr[jl + 1], dq[q + 1], dc[q + 1]), 60.f));
+            const float ic = rcp(ec0 * ec1);
+            const float c0 = fmaf(-2.0f, ic * ec1, 1.0f), c1 = fmaf(-2.0f, ic * ec0, 1.0f);
+            const float h0 = fmaf(uu[jl], hp[jl] - c0, c0), h1 = fmaf(uu[jl + 1], hp[jl + 1] - c1, c1);
+            hp[jl] = h0;
+            hp[jl + 1] = h1;
+            if (top) {
+                z0 = fmaf(h0, tab[2 * jl], z0);
+                z1 = fmaf(h0, tab[2 * jl + 1], z1);
+                z0 = fmaf(h1, tab[2 * jl + 2], z0);
+                z1 = fmaf(h1, tab[2 * jl + 3], z1);
+                if (CPLX) {
+                    y0 = fmaf(h0, tab[132 + 2 * jl], y0);
+                    y1 = fmaf(h0, tab[132 + 2 * jl + 1], y1);
+                    y0 = fmaf(h1, tab[132 + 2 * jl + 2], y0);
+                    y1 = fmaf(h1, tab[132 + 2 * jl + 3], y1);
+                }
+            }
+            if (BASE && c.live) {
+                hst[(size_t)jl * Mold] = h0;
+                hst[(size_t)(jl + 1) * Mold] = h1;
+            }
+        }
+        // region l takes the new state: it is the h operand of (n + 1, l) and the x operand of (n, l + 1), both visited later
+        stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
+    }
+    {   // unit 24 of this half, staged next to this half's share of the constant-1 column
+        float dc[1], dq[1];
+        umma::tmem_ld1p(dpart + kColCX + 24, dc);
+        umma::tmem_ld1p(dpart + kColCH + 24, dq);
+        umma::wait_ld();
+        const int jl = kUP - 1;
+        const float ec = 1.0f + ex2(fminf(fmaf(rr[jl], dq[0], dc[0]), 60.f));
+        const float cc = fmaf(-2.0f, rcp(ec), 1.0f);
+        const float h0 = fmaf(uu[jl], hp[jl] - cc, cc);
+        hp[jl] = h0;
+        if (top) {
+            z0 = fmaf(h0, tab[2 * jl], z0);
+            z1 = fmaf(h0, tab[2 * jl + 1], z1);
+            if (CPLX) {
+                y0 = fmaf(h0, tab[132 + 2 * jl], y0);
+                y1 = fmaf(h0, tab[132 + 2 * jl + 1], y1);
+            }
+        }
+        if (BASE && c.live) hst[(size_t)jl * Mold] = h0;
+        const float tail[2] = {h0, part == 0 ? 1.0f : 0.0f};
+        stage_cols<1>(reg + 12, tail);
+    }
+    if (part == 0 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
+        const int code = c.live ? spin_n : 2;
+        const float oh[1] = {__uint_as_float(pack_h2(code == 0 ? 1.f : 0.f, code == 1 ? 1.f : 0.f))};
+        umma::tmem_st1(c.lane_addr + kColR + 64 * L, oh);
+    }
+    if (top) {   // partial head sums; part 0 finishes the log-softmax at its next step (or after the chain)
+        if (part == 0) {
+            c.pz = make_float4(z0, z1, y0, y1);
+            c.pn = n;
+            c.psg = spin_n;
+            c.p_la = la_n;
+            c.p_ph = ph_n;
+            c.pph = c.cda;
+            c.pbuf = par;
+        } else {
+            c.zsm[par * kRows + c.rowi] = make_float4(z0, z1, y0, y1);
+        }
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    umma::mbar_arrive(&c.bars[kCDone]);
+    TCP_T(c.t_c += clock64() - t3;)
+    ++c.g;
+    ++c.cda;
+}
+
+// all row-thread work of one chain.  kind 0: sigma with site s flipped (TFIM); kind 1 / 2: sites s and t = s + kind exchanged
+// (J1-J2); BASE: the unmodified configuration from site 0 (s = -1).  Requires s + 1 < N.
+template <bool BASE, bool CPLX>
+__device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
+    constexpr int H = 50;
+    const int L = a.g.L, N = a.g.N, Mold = a.Mold, s = c.s, part = c.part;
+    // hidden states of this thread's 25 units: hA is the layer visited next, hB the one after it, hC the third (rotated by moves)
+    float hA[kUP], hB[kUP], hC[kUP];
+#pragma unroll
+    for (int j = 0; j < kUP; ++j) { hA[j] = 0.f; hB[j] = 0.f; hC[j] = 0.f; }
+    if (!BASE && c.live) {   // restart from the base states after site s: hA <- top layer, hB <- the layer below, ...
+        const float* src = a.hstore + ((c.rowbase + s) * L * (size_t)H + kUP * part) * Mold + c.m;
+#pragma unroll
+        for (int j = 0; j < kUP; ++j) {
+            hA[j] = src[((size_t)(L - 1) * H + j) * Mold];
+            if (L > 1) hB[j] = src[((size_t)(L - 2) * H + j) * Mold];
+            if (L > 2) hC[j] = src[(size_t)j * Mold];
+        }
+    }
+    const float one = part == 0 ? 1.0f : 0.0f;
+    const uint32_t regp = c.lane_addr + kColR + 16 * part;
+    stage_all(regp + 64 * (L - 1), hA, one);
+    if (L > 1) stage_all(regp + 64 * (L - 2), hB, one);
+    if (L > 2) stage_all(regp, hC, one);
+    c.pn = -1;
+    c.nup = 0;
+    if (part == 0) {
+        const int code = (c.live && s >= 0) ? spin_of<BASE>(a, c, s) : 2;   // input of site s + 1 (the zero vector at site 0)
+        if (CPLX && c.live && !BASE) {                                      // up spins among the sites before s + 1
+            for (int q = 0; q < s; ++q) c.nup += a.sigT[(c.rowbase + q) * Mold + c.m];
+            c.nup += code;
+        }
+        const float oh[1] = {__uint_as_float(pack_h2(code == 0 ? 1.f : 0.f, code == 1 ? 1.f : 0.f))};
+        umma::tmem_st1(c.lane_addr + kColR + 64 * L, oh);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    umma::mbar_arrive(&c.bars[kCDone]);                // "step -1": operands staged
+    ++c.cda;
+    const int n0 = s + 1;
+#pragma unroll 1
+    for (int d = n0; d <= N - 1 + L - 1; ++d) {        // anti-diagonals, top layer first
+#pragma unroll 1
+        for (int l = L - 1; l >= 0; --l) {
+            const int n = d - l;
+            if (n >= n0 && n < N) row_step<BASE, CPLX>(a, c, n, l, hA);
+            if (L == 3) {                              // (hA, hB, hC) <- (hB, hC, hA)
+#pragma unroll
+                for (int j = 0; j < kUP; ++j) { const float tmp = hA[j]; hA[j] = hB[j]; hB[j] = hC[j]; hC[j] = tmp; }
+            } else if (L == 2) {
+#pragma unroll
+                for (int j = 0; j < kUP; ++j) { const float tmp = hA[j]; hA[j] = hB[j]; hB[j] = tmp; }
+            }
+        }
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(kRowThreads) : "memory");   // part 1's partials of the last site
+    if (part == 0) finish_head<BASE, CPLX>(a, c);
+}
+
+// MMA groups of one operand (x or h) of one step; executed by every lane of the (converged) MMA warp, one elected lane issues.
+// rA: TMEM address of the operand region; consecutive instructions reuse the A chunk where they can (hi x B_hi, hi x B_lo, then
+// lo x B_hi).
+__device__ __forceinline__ void issue_part(uint32_t dcol, uint32_t rA, uint32_t b_hi, uint32_t b_lo, bool k16, uint32_t idesc, bool first_acc) {
+    if (k16) {   // one-hot input: exact in FP16, no low limb
+        umma::mma_f16_ts_elect(dcol, rA, umma::smem_desc(b_hi, 128, 2 * 128), idesc, first_acc);
+        umma::mma_f16_ts_elect(dcol, rA, umma::smem_desc(b_lo, 128, 2 * 128), idesc, 1);
+    } else {
+        const uint64_t bhi = umma::smem_desc(b_hi, 128, kKC * 128), blo = umma::smem_desc(b_lo, 128, kKC * 128);
+#pragma unroll
+        for (int ks = 0; ks < kKp / 16; ++ks) {
+            umma::mma_f16_ts_elect(dcol, rA + ks * 8, bhi + (uint64_t)(ks * 16), idesc, first_acc || ks > 0);
+            umma::mma_f16_ts_elect(dcol, rA + ks * 8, blo + (uint64_t)(ks * 16), idesc, 1);
+            umma::mma_f16_ts_elect(dcol, rA + 32 + ks * 8, bhi + (uint64_t)(ks * 16), idesc, 1);
+        }
+    }
+}
+
+template <bool BASE, bool CPLX>
+__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ Args a) {
+    extern __shared__ __align__(128) unsigned char smem_p16[];
+    const Layout& t = a.t;
+    const float* tab = reinterpret_cast<const float*>(smem_p16 + t.tab_off);
+    float4* zsm = reinterpret_cast<float4*>(smem_p16 + ((t.img_bytes + 15) & ~15));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(zsm + 2 * kRows);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+    int* s_work = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int L = a.g.L, N = a.g.N, Mold = a.Mold;
+    const bool is_row = warp < kMmaWarp;
+    const int part = warp >> 2, rowi = tid & 127;
+
+    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        umma::mbar_init(&bars[kFullRU], 1);
+        umma::mbar_init(&bars[kFullC], 1);
+        umma::mbar_init(&bars[kRuFree], kRowThreads);
+        umma::mbar_init(&bars[kCDone], kRowThreads);
+        umma::mbar_init(&bars[kWImg], 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (tid == 0) {   // the whole weight image stays resident: bulk async copies (TMA), one barrier
+        umma::mbar_expect_tx(&bars[kWImg], (uint32_t)t.img_bytes);
+        for (uint32_t o = 0; o < (uint32_t)t.img_bytes; o += 32768)
+            umma::bulk_g2s(smem_p16 + o, a.img + o, min(32768u, (uint32_t)t.img_bytes - o), &bars[kWImg]);
+    }
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    if (warp < 4) {   // zero the operand regions (the staging writes every used column, incl. the constant 1), set the constant of X0
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t c = 0; c < (uint32_t)(64 * L + 8); c += 8) umma::tmem_st8(lane_addr + kColR + c, z);
+        const float one[1] = {__uint_as_float(pack_h2(1.0f, 0.0f))};
+        umma::tmem_st1(lane_addr + kColR + 64 * L + 1, one);               // one-hot region: k = 2 is the constant 1
+        umma::wait_st();
+    }
+    if (is_row) umma::mbar_wait(&bars[kWImg], 0);                           // tab is read with ordinary loads
+    const int total = (BASE ? 1 : a.nslots) * a.tiles128;
+    const uint32_t idRU = (1u << 4) | ((uint32_t)(kNRU >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // F16 x F16 -> F32, M = 128
+    const uint32_t idC = (1u << 4) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t sB = umma::smem_u32(smem_p16);
+    bool weights_ready = false;
+    uint32_t gstep = 0, cdp = 0;             // steps done so far; c_done phases used so far (one per step + one per chain)
+    TCP_T(long long k_t0 = clock64(), k_wru = 0, k_wc = 0, k_tru = 0, k_tc = 0, k_chain = 0, k_mw1 = 0, k_mw2 = 0, k_mi = 0; int k_nch = 0;)
+
+    while (true) {
+        if (tid == 0) *s_work = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int work = *s_work;
+        __syncthreads();
+        if (work >= total) break;
+        const int tile = work % a.tiles128;
+        int slot = 0, s = -1, tt = -1;                                        // modified sites of this chain (none for BASE)
+        if (!BASE) {
+            slot = a.order ? a.order[work / a.tiles128] : work / a.tiles128;  // decreasing chain length
+            if (slot < a.nslots - a.n_kind1 - a.n_kind2) s = slot;
+            else if (slot < a.nslots - a.n_kind2) { s = slot - (a.nslots - a.n_kind1 - a.n_kind2); tt = s + 1; }
+            else { s = slot - (a.nslots - a.n_kind2); tt = s + 2; }
+            if (tt >= 0 && ((tt == s + 1 && a.j1 && a.j1[s] == 0.0) || (tt == s + 2 && a.j2 && a.j2[s] == 0.0))) continue;
+        }
+        const int64_t R = (int64_t)tile * kRows + rowi;
+        const bool live = is_row && R < a.rows_total;
+        const int64_t t120 = live ? R / Mold : 0;
+        const int m = live ? (int)(R % Mold) : 0;
+        const size_t rowbase = (size_t)t120 * N;                            // index of (old tile, site 0)
+        const int n0 = s + 1, nsteps = (N - n0) * L;
+        double acc = 0.0, acc_im = 0.0;
+        if (!BASE && live && part == 0) {
+            acc = a.la_oth[(rowbase + s) * Mold + m] - a.la_sel[(rowbase + s) * Mold + m];
+            if (CPLX) acc_im = a.ph_oth[(rowbase + s) * Mold + m] - a.ph_sel[(rowbase + s) * Mold + m];
+        }
+        if (nsteps > 0) {
+            if (is_row) {
+                Ctx c;
+                c.tab = tab; c.zsm = zsm; c.bars = bars; c.lane_addr = lane_addr; c.rowi = rowi; c.m = m; c.part = part; c.live = live;
+                c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.acc = acc; c.acc_im = acc_im;
+                c.pz = make_float4(0.f, 0.f, 0.f, 0.f); c.psg = 0; c.pn = -1; c.pph = 0; c.pbuf = 0; c.nup = 0; c.p_la = 0.0; c.p_ph = 0.0;
+                TCP_T(c.w_ru = c.w_c = c.t_ru = c.t_c = 0; long long ch0 = clock64();)
+                row_chain<BASE, CPLX>(a, c);
+                acc = c.acc; acc_im = c.acc_im;
+                TCP_T(k_wru += c.w_ru; k_wc += c.w_c; k_tru += c.t_ru; k_tc += c.t_c; k_chain += clock64() - ch0; ++k_nch;)
+            } else {   // MMA warp: all lanes stay converged, one elected lane issues
+                if (!weights_ready) { umma::mbar_wait(&bars[kWImg], 0); weights_ready = true; }
+                uint32_t g = gstep, cdw = cdp;
+                int pn = -1000, pl = -1;
+                TCP_T(long long m_w1 = 0, m_w2 = 0, m_i = 0;)
+#pragma unroll 1
+                for (int d = n0; d <= N - 1 + L - 1; ++d) {
+#pragma unroll 1
+                    for (int l = L - 1; l >= 0; --l) {
+                        const int n = d - l;
+                        if (n < n0 || n >= N) continue;
+                        // does this step consume the state produced by the step right before it?
+                        const bool dep = pn == -1000 || (pn == n && pl == l - 1) || (pn == n - 1 && pl == l);
+                        pn = n; pl = l;
+                        const uint32_t lb = sB + (l == 0 ? 0u : (uint32_t)(t.l0_bytes + (l - 1) * t.l1_bytes));
+                        const uint32_t hru_hi = lb, hru_lo = lb + t.ru_bytes, hc_hi = lb + 2 * t.ru_bytes, hc_lo = hc_hi + t.c_bytes;
+                        const uint32_t xb = lb + 2 * (t.ru_bytes + t.c_bytes);
+                        const uint32_t rub = l == 0 ? t.ru0_bytes : t.ru_bytes, cb = l == 0 ? t.c0_bytes : t.c_bytes;
+                        const uint32_t xru_hi = xb, xru_lo = xb + rub, xc_hi = xb + 2 * rub, xc_lo = xc_hi + cb;
+                        const uint32_t rX = tbase + kColR + 64 * (l == 0 ? L : l - 1), rH = tbase + kColR + 64 * l;
+                        TCP_T(long long q0 = clock64();)
+                        if (dep) umma::mbar_wait(&bars[kCDone], cdw & 1);          // previous step's state restaged
+                        else umma::mbar_wait(&bars[kRuFree], (g - 1) & 1);         // previous step's G_ru has drained D_ru
+                        umma::fence_after_sync();
+                        TCP_T(long long q1 = clock64(); m_w1 += q1 - q0;)
+#pragma unroll 1
+                        for (int e = 0; e < 4; ++e) {   // 0: x -> [r|u], 1: h -> [r|u] (accumulate), 2: x -> cx, 3: h -> ch
+                            if (e == 2) {
+                                umma::commit_elect(&bars[kFullRU]);
+                                TCP_T(long long q2 = clock64(); m_i += q2 - q1;)
+                                if (!dep) {
+                                    umma::mbar_wait(&bars[kCDone], cdw & 1);       // previous step's G_c has drained D_cx / D_ch
+                                    umma::fence_after_sync();
+                                }
+                                TCP_T(q1 = clock64(); m_w2 += q1 - q2;)
+                            }
+                            const bool xop = (e & 1) == 0, cand = e >= 2;
+                            const uint32_t dcol = tbase + (e < 2 ? kColRU : (e == 2 ? kColCX : kColCH));
+                            const uint32_t bh = cand ? (xop ? xc_hi : hc_hi) : (xop ? xru_hi : hru_hi);
+                            const uint32_t bl = cand ? (xop ? xc_lo : hc_lo) : (xop ? xru_lo : hru_lo);
+                            issue_part(dcol, xop ? rX : rH, bh, bl, xop && l == 0, cand ? idC : idRU, e == 1);
+                        }
+                        umma::commit_elect(&bars[kFullC]);
+                        TCP_T(m_i += clock64() - q1;)
+                        ++g;
+                        ++cdw;
+                    }
+                }
+                TCP_T(k_mw1 += m_w1; k_mw2 += m_w2; k_mi += m_i;)
+            }
+            __syncwarp();
+            gstep += (uint32_t)nsteps;
+            cdp += (uint32_t)nsteps + 1;
+        }
+        if (live && part == 0) {
+            if (BASE) {
+                a.lp[t120 * Mold + m] = acc;
+                if (CPLX) a.lp_im[t120 * Mold + m] = acc_im;
+            } else {
+                a.delta[((size_t)t120 * a.nslots + slot) * Mold + m] = acc;
+                if (CPLX) a.delta_im[((size_t)t120 * a.nslots + slot) * Mold + m] = acc_im;
+            }
+        }
+    }
+    TCP_T(if (gstep > 0 && !BASE) {
+        const long long tot = clock64() - k_t0;
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (tid == 0)
+            printf("tc16p blk %3d sm %3u: %6u steps %3d chains, %5lld cyc/step; wait_ru %4lld G_ru %4lld wait_c %4lld G_c %4lld; per chain outside steps %lld\n",
+                   blockIdx.x, smid, gstep, k_nch, tot / gstep, k_wru / gstep, k_tru / gstep, k_wc / gstep, k_tc / gstep,
+                   (k_chain - k_wru - k_tru - k_wc - k_tc) / k_nch);
+        if (tid == kRowThreads && (blockIdx.x % 37) == 0)
+            printf("tc16p blk %3d mma: per step wait1 %lld wait2 %lld issue %lld\n", blockIdx.x, k_mw1 / gstep, k_mw2 / gstep, k_mi / gstep);
+    })
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) umma::tmem_dealloc(tbase, 512);
+}
+
+template <bool CPLX>
+static int launch_chains(Args& a, int sms, bool flips, cudaStream_t s) {
+    const int smem = (int)smem_bytes(a.t);
+    RNNWF_CHECK(smem <= kSmemLimit, -3, "tensor-core chain kernel needs %d bytes of shared memory", smem);
+    {
+        RNNWF_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), s));
+        auto k = chain_kernel<true, CPLX>;
+        RNNWF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        prof_count();
+        k<<<std::min(a.tiles128, sms), kThreads, smem, s>>>(a);
+        RNNWF_CUDA(cudaGetLastError());
+    }
+    if (flips) {
+        RNNWF_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), s));
+        auto k = chain_kernel<false, CPLX>;
+        RNNWF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid = (int)std::min<int64_t>((int64_t)a.nslots * a.tiles128, sms);
+        prof_count();
+        prof_mark(0, s);
+        k<<<grid, kThreads, smem, s>>>(a);
+        prof_mark(1, s);
+        RNNWF_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+static Args make_args(const GruLayout& g, int Mold, int tiles, unsigned char* img, const uint8_t* sigT, float* hstore, double* la_sel,
+                      double* la_oth, double* lp, double* delta, int* counter, int& sms) {
+    int dev = 0;
+    sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    Args a;
+    memset(&a, 0, sizeof(a));
+    a.g = g; a.t = make_layout(g); a.Mold = Mold;
+    a.rows_total = (int64_t)tiles * Mold;
+    a.tiles128 = (int)cdiv(a.rows_total, kRows);
+    a.img = img; a.sigT = sigT; a.hstore = hstore; a.la_sel = la_sel; a.la_oth = la_oth; a.lp = lp; a.delta = delta; a.counter = counter;
+    a.nslots = g.N;
+    return a;
+}
+
+// base pass + single-flip chains (FP32 pRNN with 50 units)
+static int launch_eloc(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
+                       double* la_sel, double* la_oth, double* lp, double* delta, int* counter, bool flips, cudaStream_t s) {
+    int sms;
+    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, lp, delta, counter, sms);
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);
+    return launch_chains<false>(a, sms, flips, s);
+}
+
+// base pass + NN / NNN exchange chains of the complex cRNN (J1-J2); `order` lists the 2N-3 slots by decreasing chain length
+static int launch_j1j2(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
+                       double* la_sel, double* la_oth, double* ph_sel, double* ph_oth, double* lp_re, double* lp_im, double* delta_re,
+                       double* delta_im, const int* order, const double* j1, const double* j2, int* counter, cudaStream_t s) {
+    int sms;
+    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, lp_re, delta_re, counter, sms);
+    a.ph_sel = ph_sel; a.ph_oth = ph_oth; a.lp_im = lp_im; a.delta_im = delta_im; a.order = order; a.j1 = j1; a.j2 = j2;
+    a.n_kind1 = g.N - 1; a.n_kind2 = g.N - 2; a.nslots = a.n_kind1 + a.n_kind2;
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);
+    return launch_chains<true>(a, sms, true, s);
+}
+
+}  // namespace tc16p
+}  // namespace rnnwf

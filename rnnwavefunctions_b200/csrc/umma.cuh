@@ -94,6 +94,29 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
         : "memory");
 }
 
+// Warp-collective forms: EVERY lane of a converged warp executes these with identical operands, one elected lane issues.  Keeping
+// the issuing warp converged lets the compiler feed the uniform-datapath operands of UTCHMMA / UTCBAR directly instead of wrapping
+// each instruction in a lane-vote loop.
+__device__ __forceinline__ void mma_f16_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+
 // ---- TMEM <-> registers: each thread touches its own lane (32 * (warp % 4) + laneid), consecutive columns -------
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
@@ -133,6 +156,31 @@ __device__ __forceinline__ void tmem_st2(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, const float* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v[0])) : "memory");
+}
+// pointer forms used by the pipelined chain kernel (gru_tc16p.cuh)
+__device__ __forceinline__ void tmem_ld8p(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld2p(uint32_t taddr, float* v) {
+    uint32_t r[2];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(r[0]);
+    v[1] = __uint_as_float(r[1]);
+}
+__device__ __forceinline__ void tmem_ld1p(uint32_t taddr, float* v) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(r);
+}
+// one arrival (release.cta) on an mbarrier initialised with the number of arriving threads
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // store CNT (<= 8) consecutive columns starting at an 8-aligned column: 8 | 4 + 2 + 1 pieces, each size-aligned
 template <int CNT> __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const float (&v)[8]) {

@@ -1,6 +1,8 @@
 // umma_selftest.cu — known-answer check of the tcgen05 plumbing in umma.cuh (descriptor encodings, operand layouts,
 // TMEM addressing): D[128 x N] = A[128 x K] * B[N x K]^T with A staged in TMEM and B in shared memory, 1xTF32 or 3xTF32.
 // Test infrastructure for the tensor-core recurrence kernels; exposed through rnnwf_umma_selftest.
+#include <stdio.h>
+#include <stdlib.h>
 #include "api_internal.h"
 #include <cuda_fp16.h>
 #include "umma.cuh"
@@ -262,7 +264,81 @@ __global__ void __launch_bounds__(160, 1) mma_cost_kernel(int N, int count, floa
     if (out == nullptr) return;
 }
 
+// MMA cost probe 2 (development aid): like mma_cost_kernel, but B walks through `bspan` bytes of shared memory in steps of `bstride`
+// and `ldwarps` other warps stream tcgen05.ld x8 (+ optional tcgen05.st) over the accumulator columns while the MMAs run.
+__global__ void __launch_bounds__(544, 1) mma_cost2_kernel(int N, int count, int bstride, int bspan, int ldwarps, int with_st, float* out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint32_t slot;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ volatile int done;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    if (warp == 16) umma::tmem_alloc(&slot, 512);
+    if (tid == 0) { umma::mbar_init(&bar, 1); umma::mbar_fence_init(); done = 0; }
+    for (int i = tid; i < (bspan + 20480) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = slot;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    if (warp < 4) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < 64; c += 8) umma::tmem_st8(lane_addr + 300 + c, z);
+        umma::wait_st();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    float acc = 0.f;
+    if (warp == 16 && lane == 0) {
+        umma::fence_after_sync();
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t sb = umma::smem_u32(smem);
+        uint32_t off = 0;
+        const long long t0 = clock64();
+        for (int i = 0; i < count; ++i) {
+            umma::mma_f16_ts(tbase, tbase + 300 + (i & 7) * 8, umma::smem_desc(sb + off, 128, 1024), idesc, i > 0);
+            off += bstride;
+            if (off >= (uint32_t)bspan) off = 0;
+        }
+        const long long t1 = clock64();
+        umma::commit(&bar);
+        umma::mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        done = 1;
+        printf("[mma cost2] N=%3d bstride %d span %d, %d ld warps (st %d): %d MMAs issue %lld, complete %lld -> %.1f cycles/MMA\n", N, bstride, bspan,
+               ldwarps, with_st, count, t1 - t0, t2 - t0, (double)(t2 - t0) / count);
+    } else if (warp < ldwarps) {
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        long long n = 0;
+        while (!done) {
+            float a[8], b[8], c[8], d[8];
+            umma::tmem_ld8(lane_addr + 256, a);
+            umma::tmem_ld8(lane_addr + 264, b);
+            umma::tmem_ld8(lane_addr + 272, c);
+            umma::tmem_ld8(lane_addr + 280, d);
+            umma::wait_ld();
+            acc += a[0] + b[1] + c[2] + d[3];
+            if (with_st) { umma::tmem_st8(lane_addr + 400 + (warp >> 2) * 8, z); umma::wait_st(); }
+            ++n;
+        }
+        if (lane == 0 && warp == 0) printf("[mma cost2]   ld warp 0 did %lld x 4 ld8\n", n);
+    }
+    if (acc == 123.f) out[0] = acc;
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 16) umma::tmem_dealloc(tbase, 512);
+}
+
 int umma_selftest_f16_impl(int N, int K, const float* A, const float* B, float* D, int passes, int dcol, cudaStream_t s) {
+    if (const char* pe = getenv("RNNWF_PROBE")) {   // development aid: "N,count,bstride,bspan,ldwarps,with_st"
+        int pn = 112, pc = 400, pbs = 0, psp = 8192, plw = 0, pst = 0;
+        sscanf(pe, "%d,%d,%d,%d,%d,%d", &pn, &pc, &pbs, &psp, &plw, &pst);
+        const int smem = psp + 20480;
+        RNNWF_CUDA(cudaFuncSetAttribute(mma_cost2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        mma_cost2_kernel<<<1, 544, smem, s>>>(pn, pc, pbs, psp, plw, pst, D);
+        RNNWF_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (passes == 2 && dcol >= 100) {   // development aid: MMA cost probe, N = dcol - 100
         RNNWF_CUDA(cudaFuncSetAttribute(mma_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384));
         mma_cost_kernel<<<1, 160, 16384, s>>>(dcol - 100, 400, D);

@@ -33,14 +33,14 @@ print(f"sample  ns={ns}: {t:.1f} ms  mean spin {s.float().mean().item():.3f}")
 F = 75800.0
 steps = ns * N * (N + 1) / 2
 res = {}
-for chain in ("ffma", "tc32", "tc16"):
+for chain in os.environ.get("CHAINS", "ffma,tc16,tc16p").split(","):
     os.environ["RNNWF_CHAIN"] = chain
     t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
     t, (e, lp2) = timed(lambda: ops.tfim_eloc(model, flat, s, Jz, 1.0))
     res[chain] = e
     print(f"eloc[{chain:5s}] ns={ns}: {t:.1f} ms  mean E {e.mean().item():.4f}  -> {steps * F / t / 1e9:.2f} TFLOP/s algorithmic, "
           f"{ns / t * 1e3:.1f} samples/s")
-for c in ("tc32", "tc16"):
+for c in [k for k in res if k != "ffma" and "ffma" in res]:
     d = (res[c] - res["ffma"]).abs() / res["ffma"].abs()
     print(f"{c} vs ffma: max rel diff {d.max().item():.2e}")
 w = (e - e.mean()) / ns

@@ -1,4 +1,4 @@
-"""Tensor-core (tcgen05, 3xTF32) chain kernel vs the CUDA-core chain kernel and the oracle (1e-5 relative gate)."""
+"""Tensor-core (tcgen05; pipelined 3xFP16 "tc16p", 3xFP16 "tc16", 3xTF32 "tc32") chain kernels vs the CUDA-core chain kernel and the oracle (1e-5 relative gate)."""
 import os
 
 import numpy as np
@@ -33,7 +33,7 @@ def eloc_with(chain, model, flat, s, Jz, Bx, flags=0):
             os.environ["RNNWF_CHAIN"] = old
 
 
-@pytest.mark.parametrize("chain", ["tc16", "tc32"])
+@pytest.mark.parametrize("chain", ["tc16p", "tc16", "tc32"])
 @pytest.mark.parametrize("L,N,ns,parity", [(1, 20, 150, False), (3, 37, 300, False), (2, 24, 70, True), (3, 130, 260, False)])
 def test_tc_chain_matches_ffma_and_oracle(L, N, ns, parity, chain):
     units = [50] * L
@@ -66,7 +66,7 @@ def test_tc_j1j2_exchange_chains_match_ffma_and_oracle(L, N, ns, marshall, j2):
     if j2:
         J2[2] = 0.0
     out = {}
-    for chain in ("tc16", "ffma"):
+    for chain in ("tc16p", "tc16", "ffma"):
         os.environ["RNNWF_CHAIN"] = chain
         try:
             e, la = ops.j1j2_eloc(model, flat, u8(s), J1, J2, Bz, marshall_sign=marshall)
@@ -75,8 +75,9 @@ def test_tc_j1j2_exchange_chains_match_ffma_and_oracle(L, N, ns, marshall, j2):
             os.environ.pop("RNNWF_CHAIN", None)
     ref = O.j1j2_local_energies(J1, J2, Bz, s, lambda c: O.crnn_log_amplitude(p, c), marshall_sign=marshall)
     scale = max(1.0, np.abs(ref).max())
-    assert np.abs(out["tc16"][0] - out["ffma"][0]).max() < 2e-5 * scale
-    assert np.abs(out["tc16"][0] - ref).max() < 3e-5 * scale                 # the reference combine is complex64
     la_ref = O.crnn_log_amplitude(p, s)
-    np.testing.assert_allclose(out["tc16"][1].real, la_ref.real, rtol=1e-5, atol=1e-6)
-    np.testing.assert_allclose(out["tc16"][1].imag, la_ref.imag, rtol=1e-5, atol=2e-5)
+    for chain in ("tc16p", "tc16"):
+        assert np.abs(out[chain][0] - out["ffma"][0]).max() < 2e-5 * scale
+        assert np.abs(out[chain][0] - ref).max() < 3e-5 * scale              # the reference combine is complex64
+        np.testing.assert_allclose(out[chain][1].real, la_ref.real, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(out[chain][1].imag, la_ref.imag, rtol=1e-5, atol=2e-5)
