@@ -89,9 +89,10 @@ int rnnwf_tfim_eloc(const rnnwf_model* m, const void* params, const uint8_t* sam
                     const double* jz, double bx, int flags, double* eloc_out, double* logp_out,
                     void* ws, size_t ws_bytes, void* stream);
 
-/* Which chain kernel rnnwf_tfim_eloc runs for `m`: 2 = tcgen05 kind::f16 with 3xFP16 operands and resident weights
- * (FP32 probability-head GRU with 50 units, <= 3 layers), 1 = tcgen05 kind::tf32 with 3xTF32 operands, 0 = CUDA-core FFMA tile
- * engine (every other shape / dtype).  The environment variable RNNWF_CHAIN = ffma | tc32 | tc16 overrides for A/B measurements. */
+/* Which chain kernel rnnwf_tfim_eloc runs for `m`: 3 = tcgen05 kind::f16 with 3xFP16 operands, resident weights and the
+ * MMA / gate-math software pipeline (FP32 probability-head GRU with 50 units, <= 3 layers), 2 = the same arithmetic without the
+ * pipeline, 1 = tcgen05 kind::tf32 with 3xTF32 operands, 0 = CUDA-core FFMA tile engine (every other shape / dtype).  The
+ * environment variable RNNWF_CHAIN = ffma | tc32 | tc16 | tc16p overrides for A/B measurements. */
 int rnnwf_tfim_chain_mode(const rnnwf_model* m);
 
 /* Diagonal part only (bit-exact with the reference's f64 accumulation order, :31-38 / 2-D :33-49). */

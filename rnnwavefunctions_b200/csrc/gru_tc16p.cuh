@@ -41,7 +41,7 @@ using tc16::pack_h2;
 using tc16::unpack_h2;
 using tc16::core_off;
 
-constexpr int kRows = 128, kRowThreads = 256, kThreads = 288, kMmaWarp = 8;
+constexpr int kRows = 128, kRowThreads = 256, kThreads = 384, kMmaWarp = 8;   // warps 9-11 only complete the MMA warp's warpgroup (setmaxnreg)
 constexpr int kUP = 25;                                  // units per row thread (H = 50, two threads per row)
 constexpr int kBW = 56;                                  // accumulator columns per gate block
 constexpr int kNRU = 112, kNC = 64;                      // N of the M_ru / M_c instructions
@@ -350,12 +350,21 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
     const float* tab = c.tab + 2 * kUP * part;
     float* hst = BASE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kUP * part) * Mold + c.m : nullptr;
     float z0 = 0.f, z1 = 0.f, y0 = 0.f, y1 = 0.f;
+    float dcb[2][8], dqb[2][8], dct[1], dqt[1];       // accumulator loads run one unit group ahead of the math
+    umma::tmem_ld8p(dpart + kColCX, dcb[0]);
+    umma::tmem_ld8p(dpart + kColCH, dqb[0]);
 #pragma unroll
     for (int gq = 0; gq < 3; ++gq) {
-        float dc[8], dq[8];
-        umma::tmem_ld8p(dpart + kColCX + 8 * gq, dc);
-        umma::tmem_ld8p(dpart + kColCH + 8 * gq, dq);
+        const float* dc = dcb[gq & 1];
+        const float* dq = dqb[gq & 1];
         umma::wait_ld();
+        if (gq < 2) {
+            umma::tmem_ld8p(dpart + kColCX + 8 * (gq + 1), dcb[(gq + 1) & 1]);
+            umma::tmem_ld8p(dpart + kColCH + 8 * (gq + 1), dqb[(gq + 1) & 1]);
+        } else {
+            umma::tmem_ld1p(dpart + kColCX + 24, dct);
+            umma::tmem_ld1p(dpart + kColCH + 24, dqt);
+        }
 #pragma unroll
         for (int q = 0; q < 8; q += 2) {
             const int jl = 8 * gq + q;
@@ -387,12 +396,9 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
         stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
     }
     {   // unit 24 of this half, staged next to this half's share of the constant-1 column
-        float dc[1], dq[1];
-        umma::tmem_ld1p(dpart + kColCX + 24, dc);
-        umma::tmem_ld1p(dpart + kColCH + 24, dq);
         umma::wait_ld();
         const int jl = kUP - 1;
-        const float ec = 1.0f + ex2(fminf(fmaf(rr[jl], dq[0], dc[0]), 60.f));
+        const float ec = 1.0f + ex2(fminf(fmaf(rr[jl], dqt[0], dct[0]), 60.f));
         const float cc = fmaf(-2.0f, rcp(ec), 1.0f);
         const float h0 = fmaf(uu[jl], hp[jl] - cc, cc);
         hp[jl] = h0;
@@ -511,56 +517,22 @@ __device__ __forceinline__ void issue_part(uint32_t dcol, uint32_t rA, uint32_t 
     }
 }
 
-template <bool BASE, bool CPLX>
-__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ Args a) {
-    extern __shared__ __align__(128) unsigned char smem_p16[];
-    const Layout& t = a.t;
-    const float* tab = reinterpret_cast<const float*>(smem_p16 + t.tab_off);
-    float4* zsm = reinterpret_cast<float4*>(smem_p16 + ((t.img_bytes + 15) & ~15));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(zsm + 2 * kRows);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-    int* s_work = reinterpret_cast<int*>(tmem_slot + 1);
+struct Dbg { long long wru, wc, tru, tc, chain, mw1, mw2, mi; int nch; };
 
+// the persistent work loop of one warp role (ROW: the 8 row warps; otherwise the MMA warp).  Both roles execute the same
+// sequence of CTA barriers; they are separate instantiations so that each runs under its own register budget (setmaxnreg).
+template <bool BASE, bool CPLX, bool ROW, bool IDLE = false>
+__device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, float4* zsm, uint64_t* bars, int* s_work, uint32_t tbase,
+                                              uint32_t lane_addr, uint32_t sB, Dbg& dbg) {
+    const Layout& t = a.t;
     const int tid = threadIdx.x, warp = tid >> 5;
     const int L = a.g.L, N = a.g.N, Mold = a.Mold;
-    const bool is_row = warp < kMmaWarp;
     const int part = warp >> 2, rowi = tid & 127;
-
-    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, 512);
-    if (tid == 0) {
-        umma::mbar_init(&bars[kFullRU], 1);
-        umma::mbar_init(&bars[kFullC], 1);
-        umma::mbar_init(&bars[kRuFree], kRowThreads);
-        umma::mbar_init(&bars[kCDone], kRowThreads);
-        umma::mbar_init(&bars[kWImg], 1);
-        umma::mbar_fence_init();
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    if (tid == 0) {   // the whole weight image stays resident: bulk async copies (TMA), one barrier
-        umma::mbar_expect_tx(&bars[kWImg], (uint32_t)t.img_bytes);
-        for (uint32_t o = 0; o < (uint32_t)t.img_bytes; o += 32768)
-            umma::bulk_g2s(smem_p16 + o, a.img + o, min(32768u, (uint32_t)t.img_bytes - o), &bars[kWImg]);
-    }
-    const uint32_t tbase = *tmem_slot;
-    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-    if (warp < 4) {   // zero the operand regions (the staging writes every used column, incl. the constant 1), set the constant of X0
-        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (uint32_t c = 0; c < (uint32_t)(64 * L + 8); c += 8) umma::tmem_st8(lane_addr + kColR + c, z);
-        const float one[1] = {__uint_as_float(pack_h2(1.0f, 0.0f))};
-        umma::tmem_st1(lane_addr + kColR + 64 * L + 1, one);               // one-hot region: k = 2 is the constant 1
-        umma::wait_st();
-    }
-    if (is_row) umma::mbar_wait(&bars[kWImg], 0);                           // tab is read with ordinary loads
     const int total = (BASE ? 1 : a.nslots) * a.tiles128;
     const uint32_t idRU = (1u << 4) | ((uint32_t)(kNRU >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // F16 x F16 -> F32, M = 128
     const uint32_t idC = (1u << 4) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t sB = umma::smem_u32(smem_p16);
     bool weights_ready = false;
     uint32_t gstep = 0, cdp = 0;             // steps done so far; c_done phases used so far (one per step + one per chain)
-    TCP_T(long long k_t0 = clock64(), k_wru = 0, k_wc = 0, k_tru = 0, k_tc = 0, k_chain = 0, k_mw1 = 0, k_mw2 = 0, k_mi = 0; int k_nch = 0;)
-
     while (true) {
         if (tid == 0) *s_work = atomicAdd(a.counter, 1);
         __syncthreads();
@@ -577,7 +549,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             if (tt >= 0 && ((tt == s + 1 && a.j1 && a.j1[s] == 0.0) || (tt == s + 2 && a.j2 && a.j2[s] == 0.0))) continue;
         }
         const int64_t R = (int64_t)tile * kRows + rowi;
-        const bool live = is_row && R < a.rows_total;
+        const bool live = ROW && R < a.rows_total;
         const int64_t t120 = live ? R / Mold : 0;
         const int m = live ? (int)(R % Mold) : 0;
         const size_t rowbase = (size_t)t120 * N;                            // index of (old tile, site 0)
@@ -587,8 +559,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             acc = a.la_oth[(rowbase + s) * Mold + m] - a.la_sel[(rowbase + s) * Mold + m];
             if (CPLX) acc_im = a.ph_oth[(rowbase + s) * Mold + m] - a.ph_sel[(rowbase + s) * Mold + m];
         }
-        if (nsteps > 0) {
-            if (is_row) {
+        if (nsteps > 0 && !IDLE) {
+            if constexpr (ROW) {
                 Ctx c;
                 c.tab = tab; c.zsm = zsm; c.bars = bars; c.lane_addr = lane_addr; c.rowi = rowi; c.m = m; c.part = part; c.live = live;
                 c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.acc = acc; c.acc_im = acc_im;
@@ -596,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
                 TCP_T(c.w_ru = c.w_c = c.t_ru = c.t_c = 0; long long ch0 = clock64();)
                 row_chain<BASE, CPLX>(a, c);
                 acc = c.acc; acc_im = c.acc_im;
-                TCP_T(k_wru += c.w_ru; k_wc += c.w_c; k_tru += c.t_ru; k_tc += c.t_c; k_chain += clock64() - ch0; ++k_nch;)
+                TCP_T(dbg.wru += c.w_ru; dbg.wc += c.w_c; dbg.tru += c.t_ru; dbg.tc += c.t_c; dbg.chain += clock64() - ch0; ++dbg.nch;)
             } else {   // MMA warp: all lanes stay converged, one elected lane issues
                 if (!weights_ready) { umma::mbar_wait(&bars[kWImg], 0); weights_ready = true; }
                 uint32_t g = gstep, cdw = cdp;
@@ -645,9 +617,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
                         ++cdw;
                     }
                 }
-                TCP_T(k_mw1 += m_w1; k_mw2 += m_w2; k_mi += m_i;)
+                TCP_T(dbg.mw1 += m_w1; dbg.mw2 += m_w2; dbg.mi += m_i;)
             }
-            __syncwarp();
             gstep += (uint32_t)nsteps;
             cdp += (uint32_t)nsteps + 1;
         }
@@ -661,16 +632,75 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             }
         }
     }
+    return gstep;
+}
+
+template <bool BASE, bool CPLX>
+__global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ Args a) {
+    extern __shared__ __align__(128) unsigned char smem_p16[];
+    const Layout& t = a.t;
+    const float* tab = reinterpret_cast<const float*>(smem_p16 + t.tab_off);
+    float4* zsm = reinterpret_cast<float4*>(smem_p16 + ((t.img_bytes + 15) & ~15));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(zsm + 2 * kRows);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+    int* s_work = reinterpret_cast<int*>(tmem_slot + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int L = a.g.L;
+    const bool is_row = warp < kMmaWarp;
+
+    if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        umma::mbar_init(&bars[kFullRU], 1);
+        umma::mbar_init(&bars[kFullC], 1);
+        umma::mbar_init(&bars[kRuFree], kRowThreads);
+        umma::mbar_init(&bars[kCDone], kRowThreads);
+        umma::mbar_init(&bars[kWImg], 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    if (tid == 0) {   // the whole weight image stays resident: bulk async copies (TMA), one barrier
+        umma::mbar_expect_tx(&bars[kWImg], (uint32_t)t.img_bytes);
+        for (uint32_t o = 0; o < (uint32_t)t.img_bytes; o += 32768)
+            umma::bulk_g2s(smem_p16 + o, a.img + o, min(32768u, (uint32_t)t.img_bytes - o), &bars[kWImg]);
+    }
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t lane_addr = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+    if (warp < 4) {   // zero the operand regions (the staging writes every used column, incl. the constant 1), set the constant of X0
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (uint32_t c = 0; c < (uint32_t)(64 * L + 8); c += 8) umma::tmem_st8(lane_addr + kColR + c, z);
+        const float one[1] = {__uint_as_float(pack_h2(1.0f, 0.0f))};
+        umma::tmem_st1(lane_addr + kColR + 64 * L + 1, one);               // one-hot region: k = 2 is the constant 1
+        umma::wait_st();
+    }
+    if (is_row) umma::mbar_wait(&bars[kWImg], 0);                           // tab is read with ordinary loads
+    const uint32_t sB = umma::smem_u32(smem_p16);
+    Dbg dbg;
+    memset(&dbg, 0, sizeof(dbg));
+    TCP_T(const long long k_t0 = clock64();)
+    // register budgets per role: the kernel is compiled for 168 registers per thread (3 warps of an SM sub-partition must fit);
+    // the MMA warp hands most of its share to the row warps, which keep three layers' hidden states in registers
+    uint32_t gstep;
+    if (is_row) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        gstep = work_loop<BASE, CPLX, true>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == kMmaWarp) gstep = work_loop<BASE, CPLX, false>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
+        else gstep = work_loop<BASE, CPLX, false, true>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);   // CTA barriers only
+    }
     TCP_T(if (gstep > 0 && !BASE) {
         const long long tot = clock64() - k_t0;
         unsigned smid;
         asm("mov.u32 %0, %%smid;" : "=r"(smid));
         if (tid == 0)
             printf("tc16p blk %3d sm %3u: %6u steps %3d chains, %5lld cyc/step; wait_ru %4lld G_ru %4lld wait_c %4lld G_c %4lld; per chain outside steps %lld\n",
-                   blockIdx.x, smid, gstep, k_nch, tot / gstep, k_wru / gstep, k_tru / gstep, k_wc / gstep, k_tc / gstep,
-                   (k_chain - k_wru - k_tru - k_wc - k_tc) / k_nch);
+                   blockIdx.x, smid, gstep, dbg.nch, tot / gstep, dbg.wru / gstep, dbg.tru / gstep, dbg.wc / gstep, dbg.tc / gstep,
+                   (dbg.chain - dbg.wru - dbg.tru - dbg.wc - dbg.tc) / dbg.nch);
         if (tid == kRowThreads && (blockIdx.x % 37) == 0)
-            printf("tc16p blk %3d mma: per step wait1 %lld wait2 %lld issue %lld\n", blockIdx.x, k_mw1 / gstep, k_mw2 / gstep, k_mi / gstep);
+            printf("tc16p blk %3d mma: per step wait1 %lld wait2 %lld issue %lld\n", blockIdx.x, dbg.mw1 / gstep, dbg.mw2 / gstep, dbg.mi / gstep);
     })
     umma::fence_before_sync();
     __syncthreads();

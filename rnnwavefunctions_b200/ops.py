@@ -117,7 +117,7 @@ def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
 
 
 def tfim_chain_mode(model) -> int:
-    """2: tcgen05 3xFP16 chain kernel, 1: tcgen05 3xTF32, 0: CUDA-core FFMA (see include/rnnwf.h)."""
+    """3: pipelined tcgen05 3xFP16 chain kernel, 2: unpipelined 3xFP16, 1: tcgen05 3xTF32, 0: CUDA-core FFMA (see include/rnnwf.h)."""
     return int(_lib.load().rnnwf_tfim_chain_mode(C.byref(model)))
 
 

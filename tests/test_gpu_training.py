@@ -100,11 +100,11 @@ def test_run_1dtfim_converges_to_exact(tmp_path, golden):
 
 
 def test_run_1dtfim_tensor_core_path_converges(tmp_path):
-    # 50 units: rnnwf_tfim_eloc runs the tcgen05 3xFP16 chain kernel; the optimisation must reach the free-fermion ground state
+    # 50 units: rnnwf_tfim_eloc runs the (pipelined) tcgen05 3xFP16 chain kernel; the optimisation must reach the free-fermion ground state
     from rnnwavefunctions_b200 import ops
     N = 16
     model = ops.make_model(num_layers=2, units=50, n_sites=N)
-    assert ops.tfim_chain_mode(model) == 2
+    assert ops.tfim_chain_mode(model) == 3                                # 3: pipelined 3xFP16 tcgen05 kernel (gru_tc16p.cuh)
     exact = O.tfim1d_exact_energy(N, 1.0, 1.0)
     E, V = TR.run_1DTFIM(numsteps=400, systemsize=N, num_units=50, Bx=1, num_layers=2, numsamples=500, learningrate=5e-3, seed=7,
                          save=False, verbose=False)
