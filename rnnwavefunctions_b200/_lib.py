@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librnnwf_b200.so")
+LIB_PATH = os.environ.get("RNNWF_LIB") or os.path.join(HERE, "librnnwf_b200.so")   # RNNWF_LIB: A/B builds while developing
 
 CELL_GRU, CELL_MDRNN = 0, 1
 HEAD_PROB, HEAD_COMPLEX = 0, 1

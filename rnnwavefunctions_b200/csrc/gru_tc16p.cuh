@@ -21,16 +21,28 @@
 //     first TPC of each GPC at 4 500 cycles per step, the others at 6 500 - 10 000).  The two row threads of a sample own 25
 //     units each, placed at aligned TMEM columns so that the same instructions work for either half with a runtime offset;
 //     the per-layer hidden-state registers are rotated with moves instead of unrolling the layer loop.
-// TMEM columns: D_r [0,56) D_u [56,112) | D_cx [112,176) | D_ch [176,240) | R_l (h^l: 32 hi + 32 lo packed half pairs) at 240 + 64 l |
-//               X0 (one-hot input of layer 0) at 240 + 64 L.
+// Generation 3b: the x operand feeds ONE instruction group [cx | r | u] (N = 176) and the h operand ONE group [r | u | ch]
+// (N = 176): a tcgen05.mma with a new A chunk costs ~81 cycles of TMEM operand fetch whatever its N (scripts/mma_probe2.py), so
+// 24 wide instructions (~2 150 cycles per step, tensor-throughput bound) replace 48 narrow ones (~3 300, operand-fetch bound).
+// One commit per step; the row warps pull the whole accumulator set into registers first, release it (acc_free) and do all the
+// gate math while the tensor pipe already runs the next step.
+// TMEM columns: junk [0,8) | D_cx [8,64) | D_r [64,120) D_u [120,176) | D_ch [176,232) | junk [232,240) |
+//               R_l (h^l: 32 hi + 32 lo packed half pairs) at 240 + 64 l | X0 (one-hot input of layer 0) at 240 + 64 L.
 //   gate block (56 columns): unit j < 25 at column j, unit j >= 25 at column j + 3 (second half starts at 28)
 //   operand region (K = 64):  unit j < 25 at k = j, the constant 1 (bias column) at k = 25, unit j >= 25 at k = j + 7 (32..56)
-// Shared memory: per layer the K-major core-matrix images HRU_hi | HRU_lo | HC_hi | HC_lo | XRU_hi | XRU_lo | XC_hi | XC_lo
-// (RU: 112 rows = [r(56) | u(56)], C: 56 rows; the N = 64 candidate MMAs run 8 rows into whatever follows — those rows only
-// produce accumulator columns nobody reads).
+// Shared memory: per layer the K-major core-matrix images H_hi | H_lo | X_hi | X_lo, 168 rows each: H = [r(56) | u(56) | ch(56)],
+// X = [cx(56) | r(56) | u(56)].  The N = 176 instructions of the h operand run 8 rows (one row group) into whatever follows the
+// image, those of the x operand START one row group before it: the stray rows only feed the junk accumulator columns.
 // Included by gru.cu.
 #pragma once
 #include "gru_tc16.cuh"
+
+#ifndef RNNWF_GATES
+#define RNNWF_GATES 0
+#endif
+#ifndef RNNWF_CAND
+#define RNNWF_CAND 0
+#endif
 
 namespace rnnwf {
 namespace tc16p {
@@ -44,19 +56,19 @@ using tc16::core_off;
 constexpr int kRows = 128, kRowThreads = 256, kThreads = 384, kMmaWarp = 8;   // warps 9-11 only complete the MMA warp's warpgroup (setmaxnreg)
 constexpr int kUP = 25;                                  // units per row thread (H = 50, two threads per row)
 constexpr int kBW = 56;                                  // accumulator columns per gate block
-constexpr int kNRU = 112, kNC = 64;                      // N of the M_ru / M_c instructions
-constexpr int kRowsRU = 112, kRowsC = 56;                // stored B rows of the [r | u] and candidate images
+constexpr int kNAll = 176, kNRU = 112, kNC = 64;         // N of the merged instructions; of the two that open the h group
+constexpr int kRowsImg = 168;                            // stored B rows of an image: three gate blocks
 constexpr int kKp = 64, kKC = 8;                         // K padded to 4 MMA steps of 16; 16-byte chunks per row
-constexpr int kColRU = 0, kColCX = 112, kColCH = 176, kColR = 240;
+constexpr int kColX = 0, kColCX = 8, kColRU = 64, kColCH = 176, kColR = 240;   // kColX: D base of the x group (junk | cx | r | u)
 constexpr int kKOne = kUP;                               // K index of the constant-1 (bias) column
-enum { kFullRU = 0, kFullC = 1, kRuFree = 2, kCDone = 3, kWImg = 4, kNumBars = 5 };
+enum { kFull = 0, kAccFree = 1, kCDone = 2, kWImg = 3, kNumBars = 4 };
 
 __host__ __device__ __forceinline__ int unit_of_col(int c) { return c < kUP ? c : (c >= 28 && c < 28 + kUP ? c - 3 : -1); }   // gate-block column -> unit
 __host__ __device__ __forceinline__ int unit_of_k(int k) { return k < kUP ? k : (k >= 32 && k < 32 + kUP ? k - 7 : -1); }     // operand K index -> unit
 
 struct Layout {
     int L, H, N;
-    int ru_bytes, c_bytes, ru0_bytes, c0_bytes;   // one precision half of an [r|u] / candidate image with K = 64 / K = 16 (layer 0 input)
+    int im_bytes, im0_bytes;                      // one precision half of an image with K = 64 / K = 16 (layer 0 input)
     int l0_bytes, l1_bytes;
     int tab_off, tab_floats, img_bytes;
 };
@@ -64,12 +76,10 @@ struct Layout {
 inline Layout make_layout(const GruLayout& g) {
     Layout t;
     t.L = g.L; t.H = g.H; t.N = g.N;
-    t.ru_bytes = kRowsRU * kKp * 2;
-    t.c_bytes = kRowsC * kKp * 2;
-    t.ru0_bytes = kRowsRU * 16 * 2;
-    t.c0_bytes = kRowsC * 16 * 2;
-    t.l0_bytes = 2 * (t.ru_bytes + t.c_bytes) + 2 * (t.ru0_bytes + t.c0_bytes);
-    t.l1_bytes = 4 * (t.ru_bytes + t.c_bytes);
+    t.im_bytes = kRowsImg * kKp * 2;
+    t.im0_bytes = kRowsImg * 16 * 2;
+    t.l0_bytes = 2 * t.im_bytes + 2 * t.im0_bytes;
+    t.l1_bytes = 4 * t.im_bytes;
     t.tab_off = t.l0_bytes + (g.L - 1) * t.l1_bytes;
     t.tab_floats = g.nheads * (2 * 64 + 4);       // per head: Wd[64][2] | bd[2] | pad
     t.img_bytes = t.tab_off + t.tab_floats * 4;
@@ -93,14 +103,13 @@ inline bool supported(const GruLayout& g) {
 __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ flat, unsigned char* __restrict__ img) {
     const int H = g.H;
     const float kS = -1.4426950408889634f, kC = 2.8853900817779268f;
-    constexpr int kRowsAll = kRowsRU + kRowsC;          // 168 stored rows per (layer, part)
-    const int per_l = 2 * kRowsAll * kKp;               // h part + x part
+    const int per_l = 2 * kRowsImg * kKp;               // h image + x image
     const int total = g.L * per_l;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int l = idx / per_l;
         int q = idx % per_l;
-        const int xpart = q / (kRowsAll * kKp);
-        q %= kRowsAll * kKp;
+        const int xpart = q / (kRowsImg * kKp);
+        q %= kRowsImg * kKp;
         const int n = q / kKp, k = q % kKp;
         const int d = g.d[l];
         const float* Kg = flat + g.flat_off[l];
@@ -110,44 +119,43 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         const float* bci = Kch + H * H;
         const float* bch = bci + H;
         unsigned char* Lb = img + (l == 0 ? 0 : t.l0_bytes + (l - 1) * t.l1_bytes);
-        const bool ru = n < kRowsRU;
-        const int gate = ru ? n / kBW : 0;
-        const int j = unit_of_col(ru ? n % kBW : n - kRowsRU);   // output unit of this row (-1: padding)
-        const int nn = ru ? n : n - kRowsRU;                     // row inside its image
+        // gate blocks: h image [r | u | ch], x image [cx | r | u]
+        const int blk = n / kBW;
+        const bool cand = xpart ? blk == 0 : blk == 2;
+        const int gate = xpart ? blk - 1 : blk;                  // 0: r, 1: u (unused for the candidate block)
+        const int j = unit_of_col(n % kBW);                      // output unit of this row (-1: padding)
         const int ku = unit_of_k(k);                             // input unit of this K index (-1: constant / padding)
         float v = 0.f;
         int KC = kKC;
         unsigned char *hi_b, *lo_b;
         if (!xpart) {
             if (j >= 0) {
-                if (ru) v = ku >= 0 ? kS * Kg[(d + ku) * 2 * H + gate * H + j] : (k == kKOne ? kS * bg[gate * H + j] : 0.f);
+                if (!cand) v = ku >= 0 ? kS * Kg[(d + ku) * 2 * H + gate * H + j] : (k == kKOne ? kS * bg[gate * H + j] : 0.f);
                 else v = ku >= 0 ? kC * Kch[ku * H + j] : (k == kKOne ? kC * bch[j] : 0.f);
             }
-            hi_b = Lb + (ru ? 0 : 2 * t.ru_bytes);
-            lo_b = hi_b + (ru ? t.ru_bytes : t.c_bytes);
+            hi_b = Lb;
+            lo_b = Lb + t.im_bytes;
         } else {
-            unsigned char* Xb = Lb + 2 * (t.ru_bytes + t.c_bytes);
+            hi_b = Lb + 2 * t.im_bytes;
             if (l > 0) {
                 if (j >= 0) {
-                    if (ru) v = ku >= 0 ? kS * Kg[ku * 2 * H + gate * H + j] : 0.f;
+                    if (!cand) v = ku >= 0 ? kS * Kg[ku * 2 * H + gate * H + j] : 0.f;
                     else v = ku >= 0 ? kC * Kci[ku * H + j] : (k == kKOne ? kC * bci[j] : 0.f);
                 }
-                hi_b = Xb + (ru ? 0 : 2 * t.ru_bytes);
-                lo_b = hi_b + (ru ? t.ru_bytes : t.c_bytes);
+                lo_b = hi_b + t.im_bytes;
             } else {
                 if (k >= 16) continue;
                 KC = 2;
                 if (j >= 0) {
-                    if (ru) v = k < 2 ? kS * Kg[k * 2 * H + gate * H + j] : 0.f;
+                    if (!cand) v = k < 2 ? kS * Kg[k * 2 * H + gate * H + j] : 0.f;
                     else v = k < 2 ? kC * Kci[k * H + j] : (k == 2 ? kC * bci[j] : 0.f);
                 }
-                hi_b = Xb + (ru ? 0 : 2 * t.ru0_bytes);
-                lo_b = hi_b + (ru ? t.ru0_bytes : t.c0_bytes);
+                lo_b = hi_b + t.im0_bytes;
             }
         }
         const __half hi = __float2half_rn(v);
-        reinterpret_cast<__half*>(hi_b)[core_off(nn, k, KC)] = hi;
-        reinterpret_cast<__half*>(lo_b)[core_off(nn, k, KC)] = __float2half_rn(v - __half2float(hi));
+        reinterpret_cast<__half*>(hi_b)[core_off(n, k, KC)] = hi;
+        reinterpret_cast<__half*>(lo_b)[core_off(n, k, KC)] = __float2half_rn(v - __half2float(hi));
     }
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < t.tab_floats; idx += gridDim.x * blockDim.x) {
         const int hd = idx / 132, r = idx % 132;        // per head: Wd[j][2] (64 x 2) | bd[2] | pad
@@ -288,7 +296,8 @@ template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(cons
     }
 }
 
-// one (site n, layer l) step of a row thread: G_ru on D_ru, then G_c on D_cx / D_ch + restaging of the new state.
+// one (site n, layer l) step of a row thread: pull the step's accumulators out of TMEM, release them to the MMA warp, then
+// reset / update gates, candidate, new state, head partial sums and restaging from registers.
 // hp: this thread's 25 units of h^l (previous site in, this site out).
 template <bool BASE, bool CPLX>
 __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, float* hp) {
@@ -297,7 +306,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
     const bool top = l == L - 1;
     const uint32_t par = c.g & 1;
     const uint32_t dpart = c.lane_addr + 28 * part;                       // this thread's columns inside a gate block
-    // global loads this step will need at its end are issued before the first wait (part 0): the spin of site n (one-hot input of
+    // global loads this step will need at its end are issued before the wait (part 0): the spin of site n (one-hot input of
     // (n + 1, 0) / selected outcome of the head) and the base-pass terms of site n
     int spin_n = 0;
     double la_n = 0.0, ph_n = 0.0;
@@ -308,13 +317,11 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
             if (CPLX) ph_n = a.ph_sel[(c.rowbase + n) * Mold + c.m];
         }
     }
-    // ---- G_ru: reset / update gates.  Two units at a time: 1/(1+2^a) for r0, u0, r1, u1 share ONE reciprocal (exponents
-    // clamped to 30, so the product of the four denominators stays below 2^121)
     TCP_T(long long t0 = clock64();)
-    umma::mbar_wait(&c.bars[kFullRU], par);
+    umma::mbar_wait(&c.bars[kFull], par);
     umma::fence_after_sync();
     TCP_T(long long t1 = clock64(); c.w_ru += t1 - t0;)
-    float rr[kUP], uu[kUP];
+    float rr[kUP], uu[kUP], dc[kUP], dq[kUP];
 #pragma unroll
     for (int gq = 0; gq < 3; ++gq) {
         umma::tmem_ld8p(dpart + kColRU + 8 * gq, rr + 8 * gq);
@@ -322,9 +329,23 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
     }
     umma::tmem_ld1p(dpart + kColRU + 24, rr + 24);
     umma::tmem_ld1p(dpart + kColRU + kBW + 24, uu + 24);
+#pragma unroll
+    for (int gq = 0; gq < 3; ++gq) {
+        umma::tmem_ld8p(dpart + kColCX + 8 * gq, dc + 8 * gq);
+        umma::tmem_ld8p(dpart + kColCH + 8 * gq, dq + 8 * gq);
+    }
+    umma::tmem_ld1p(dpart + kColCX + 24, dc + 24);
+    umma::tmem_ld1p(dpart + kColCH + 24, dq + 24);
     umma::wait_ld();
     umma::fence_before_sync();
-    umma::mbar_arrive(&c.bars[kRuFree]);               // D_ru may be overwritten by the next step's M_ru
+    umma::mbar_arrive(&c.bars[kAccFree]);              // the accumulators may be overwritten by the next step's MMAs
+    TCP_T(long long t2 = clock64(); c.w_c += t2 - t1;)
+    if (part == 0) finish_head<BASE, CPLX>(a, c);
+    // ---- reset / update gates 1/(1 + 2^a).  RNNWF_GATES selects how many reciprocals are shared (MUFU pipe against issue slots):
+    // 0: r0, u0, r1, u1 of two units share ONE reciprocal (exponents clamped to 30, so the product of the four denominators stays
+    //    below 2^121): 2.5 MUFU and 11 instructions per unit;  1: one reciprocal per gate (ex2(+big) = inf -> 1/inf = 0, no clamps):
+    //    4 MUFU, 6 instructions;  2: r and u of a unit share a reciprocal: 3 MUFU, 10 instructions
+#if RNNWF_GATES == 0
 #pragma unroll
     for (int q = 0; q < kUP - 1; q += 2) {
         const float er0 = 1.0f + ex2(fminf(rr[q], 30.f)), eu0 = 1.0f + ex2(fminf(uu[q], 30.f));
@@ -340,38 +361,41 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
         const float inv = rcp(er * eu);
         rr[kUP - 1] = inv * eu; uu[kUP - 1] = inv * er;
     }
-    // ---- G_c: candidate, new state, head partial sums, restaging
-    TCP_T(long long t2 = clock64(); c.t_ru += t2 - t1;)
-    umma::mbar_wait(&c.bars[kFullC], par);
-    umma::fence_after_sync();
-    TCP_T(long long t3 = clock64(); c.w_c += t3 - t2;)
-    if (part == 0) finish_head<BASE, CPLX>(a, c);
+#elif RNNWF_GATES == 1
+#pragma unroll
+    for (int q = 0; q < kUP; ++q) {
+        rr[q] = rcp(1.0f + ex2(rr[q]));
+        uu[q] = rcp(1.0f + ex2(uu[q]));
+    }
+#else
+#pragma unroll
+    for (int q = 0; q < kUP; ++q) {
+        const float er = 1.0f + ex2(fminf(rr[q], 60.f)), eu = 1.0f + ex2(fminf(uu[q], 60.f));
+        const float inv = rcp(er * eu);
+        rr[q] = inv * eu; uu[q] = inv * er;
+    }
+#endif
+    TCP_T(long long t3 = clock64(); c.t_ru += t3 - t2;)
+    // ---- candidate, new state, head partial sums, restaging
     const uint32_t reg = c.lane_addr + kColR + 64 * l + 16 * part;
     const float* tab = c.tab + 2 * kUP * part;
     float* hst = BASE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kUP * part) * Mold + c.m : nullptr;
     float z0 = 0.f, z1 = 0.f, y0 = 0.f, y1 = 0.f;
-    float dcb[2][8], dqb[2][8], dct[1], dqt[1];       // accumulator loads run one unit group ahead of the math
-    umma::tmem_ld8p(dpart + kColCX, dcb[0]);
-    umma::tmem_ld8p(dpart + kColCH, dqb[0]);
 #pragma unroll
     for (int gq = 0; gq < 3; ++gq) {
-        const float* dc = dcb[gq & 1];
-        const float* dq = dqb[gq & 1];
-        umma::wait_ld();
-        if (gq < 2) {
-            umma::tmem_ld8p(dpart + kColCX + 8 * (gq + 1), dcb[(gq + 1) & 1]);
-            umma::tmem_ld8p(dpart + kColCH + 8 * (gq + 1), dqb[(gq + 1) & 1]);
-        } else {
-            umma::tmem_ld1p(dpart + kColCX + 24, dct);
-            umma::tmem_ld1p(dpart + kColCH + 24, dqt);
-        }
 #pragma unroll
         for (int q = 0; q < 8; q += 2) {
             const int jl = 8 * gq + q;
-            const float ec0 = 1.0f + ex2(fminf(fmaf(rr[jl], dq[q], dc[q]), 60.f));
-            const float ec1 = 1.0f + ex2(fminf(fmaf(rr[jl + 1], dq[q + 1], dc[q + 1]), 60.f));
+            // candidate tanh(x) = 1 - 2 / (1 + 2^a), a = 2 log2(e) x.  RNNWF_CAND 0: two units share a reciprocal, 1: one each
+#if RNNWF_CAND == 0
+            const float ec0 = 1.0f + ex2(fminf(fmaf(rr[jl], dq[jl], dc[jl]), 60.f));
+            const float ec1 = 1.0f + ex2(fminf(fmaf(rr[jl + 1], dq[jl + 1], dc[jl + 1]), 60.f));
             const float ic = rcp(ec0 * ec1);
             const float c0 = fmaf(-2.0f, ic * ec1, 1.0f), c1 = fmaf(-2.0f, ic * ec0, 1.0f);
+#else
+            const float c0 = fmaf(-2.0f, rcp(1.0f + ex2(fmaf(rr[jl], dq[jl], dc[jl]))), 1.0f);
+            const float c1 = fmaf(-2.0f, rcp(1.0f + ex2(fmaf(rr[jl + 1], dq[jl + 1], dc[jl + 1]))), 1.0f);
+#endif
             const float h0 = fmaf(uu[jl], hp[jl] - c0, c0), h1 = fmaf(uu[jl + 1], hp[jl + 1] - c1, c1);
             hp[jl] = h0;
             hp[jl + 1] = h1;
@@ -396,9 +420,8 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
         stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
     }
     {   // unit 24 of this half, staged next to this half's share of the constant-1 column
-        umma::wait_ld();
         const int jl = kUP - 1;
-        const float ec = 1.0f + ex2(fminf(fmaf(rr[jl], dqt[0], dct[0]), 60.f));
+        const float ec = 1.0f + ex2(fminf(fmaf(rr[jl], dq[jl], dc[jl]), 60.f));
         const float cc = fmaf(-2.0f, rcp(ec), 1.0f);
         const float h0 = fmaf(uu[jl], hp[jl] - cc, cc);
         hp[jl] = h0;
@@ -499,20 +522,40 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
     if (part == 0) finish_head<BASE, CPLX>(a, c);
 }
 
-// MMA groups of one operand (x or h) of one step; executed by every lane of the (converged) MMA warp, one elected lane issues.
-// rA: TMEM address of the operand region; consecutive instructions reuse the A chunk where they can (hi x B_hi, hi x B_lo, then
-// lo x B_hi).
-__device__ __forceinline__ void issue_part(uint32_t dcol, uint32_t rA, uint32_t b_hi, uint32_t b_lo, bool k16, uint32_t idesc, bool first_acc) {
-    if (k16) {   // one-hot input: exact in FP16, no low limb
-        umma::mma_f16_ts_elect(dcol, rA, umma::smem_desc(b_hi, 128, 2 * 128), idesc, first_acc);
-        umma::mma_f16_ts_elect(dcol, rA, umma::smem_desc(b_lo, 128, 2 * 128), idesc, 1);
+// the MMA instructions of one (site, layer) step; executed by every lane of the (converged) MMA warp, one elected lane issues.
+// x group: D[junk | cx | r | u] = x * X^T (overwrite), h group: D[r | u | ch | junk] += h * H^T, where the very first h
+// instruction is split in two because it accumulates onto r, u but must overwrite ch.  Consecutive instructions reuse the A chunk
+// where they can (hi x B_hi, hi x B_lo, then lo x B_hi).
+__device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t rH, uint32_t x_hi, uint32_t x_lo, uint32_t h_hi, uint32_t h_lo,
+                                           bool k16) {
+    constexpr uint32_t idAll = (1u << 4) | ((uint32_t)(kNAll >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F16 x F16 -> F32, M = 128
+    constexpr uint32_t idRU = (1u << 4) | ((uint32_t)(kNRU >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idC = (1u << 4) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t dX = tbase + kColX, dH = tbase + kColRU, dCH = tbase + kColCH;
+    if (k16) {   // one-hot input: exact in FP16, no low limb; the x images start one row group (8 rows x 32 bytes) early
+        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_hi - 256, 128, 2 * 128), idAll, 0);
+        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_lo - 256, 128, 2 * 128), idAll, 1);
     } else {
-        const uint64_t bhi = umma::smem_desc(b_hi, 128, kKC * 128), blo = umma::smem_desc(b_lo, 128, kKC * 128);
+        const uint64_t bhi = umma::smem_desc(x_hi - kKC * 128, 128, kKC * 128), blo = umma::smem_desc(x_lo - kKC * 128, 128, kKC * 128);
 #pragma unroll
         for (int ks = 0; ks < kKp / 16; ++ks) {
-            umma::mma_f16_ts_elect(dcol, rA + ks * 8, bhi + (uint64_t)(ks * 16), idesc, first_acc || ks > 0);
-            umma::mma_f16_ts_elect(dcol, rA + ks * 8, blo + (uint64_t)(ks * 16), idesc, 1);
-            umma::mma_f16_ts_elect(dcol, rA + 32 + ks * 8, bhi + (uint64_t)(ks * 16), idesc, 1);
+            umma::mma_f16_ts_elect(dX, rX + ks * 8, bhi + (uint64_t)(ks * 16), idAll, ks > 0);
+            umma::mma_f16_ts_elect(dX, rX + ks * 8, blo + (uint64_t)(ks * 16), idAll, 1);
+            umma::mma_f16_ts_elect(dX, rX + 32 + ks * 8, bhi + (uint64_t)(ks * 16), idAll, 1);
+        }
+    }
+    {
+        const uint64_t bhi = umma::smem_desc(h_hi, 128, kKC * 128), blo = umma::smem_desc(h_lo, 128, kKC * 128);
+        const uint64_t bch = umma::smem_desc(h_hi + 2 * kBW * kKp * 2, 128, kKC * 128);          // candidate rows of H_hi
+        umma::mma_f16_ts_elect(dH, rH, bhi, idRU, 1);
+        umma::mma_f16_ts_elect(dCH, rH, bch, idC, 0);
+        umma::mma_f16_ts_elect(dH, rH, blo, idAll, 1);
+        umma::mma_f16_ts_elect(dH, rH + 32, bhi, idAll, 1);
+#pragma unroll
+        for (int ks = 1; ks < kKp / 16; ++ks) {
+            umma::mma_f16_ts_elect(dH, rH + ks * 8, bhi + (uint64_t)(ks * 16), idAll, 1);
+            umma::mma_f16_ts_elect(dH, rH + ks * 8, blo + (uint64_t)(ks * 16), idAll, 1);
+            umma::mma_f16_ts_elect(dH, rH + 32 + ks * 8, bhi + (uint64_t)(ks * 16), idAll, 1);
         }
     }
 }
@@ -529,8 +572,6 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
     const int L = a.g.L, N = a.g.N, Mold = a.Mold;
     const int part = warp >> 2, rowi = tid & 127;
     const int total = (BASE ? 1 : a.nslots) * a.tiles128;
-    const uint32_t idRU = (1u << 4) | ((uint32_t)(kNRU >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);    // F16 x F16 -> F32, M = 128
-    const uint32_t idC = (1u << 4) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     bool weights_ready = false;
     uint32_t gstep = 0, cdp = 0;             // steps done so far; c_done phases used so far (one per step + one per chain)
     while (true) {
@@ -584,35 +625,18 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
                         const bool dep = pn == -1000 || (pn == n && pl == l - 1) || (pn == n - 1 && pl == l);
                         pn = n; pl = l;
                         const uint32_t lb = sB + (l == 0 ? 0u : (uint32_t)(t.l0_bytes + (l - 1) * t.l1_bytes));
-                        const uint32_t hru_hi = lb, hru_lo = lb + t.ru_bytes, hc_hi = lb + 2 * t.ru_bytes, hc_lo = hc_hi + t.c_bytes;
-                        const uint32_t xb = lb + 2 * (t.ru_bytes + t.c_bytes);
-                        const uint32_t rub = l == 0 ? t.ru0_bytes : t.ru_bytes, cb = l == 0 ? t.c0_bytes : t.c_bytes;
-                        const uint32_t xru_hi = xb, xru_lo = xb + rub, xc_hi = xb + 2 * rub, xc_lo = xc_hi + cb;
+                        const uint32_t h_hi = lb, h_lo = lb + t.im_bytes, x_hi = lb + 2 * t.im_bytes;
+                        const uint32_t x_lo = x_hi + (l == 0 ? t.im0_bytes : t.im_bytes);
                         const uint32_t rX = tbase + kColR + 64 * (l == 0 ? L : l - 1), rH = tbase + kColR + 64 * l;
                         TCP_T(long long q0 = clock64();)
-                        if (dep) umma::mbar_wait(&bars[kCDone], cdw & 1);          // previous step's state restaged
-                        else umma::mbar_wait(&bars[kRuFree], (g - 1) & 1);         // previous step's G_ru has drained D_ru
-                        umma::fence_after_sync();
+                        umma::mbar_wait(&bars[kAccFree], (g - 1) & 1);             // previous step's accumulators are in registers
                         TCP_T(long long q1 = clock64(); m_w1 += q1 - q0;)
-#pragma unroll 1
-                        for (int e = 0; e < 4; ++e) {   // 0: x -> [r|u], 1: h -> [r|u] (accumulate), 2: x -> cx, 3: h -> ch
-                            if (e == 2) {
-                                umma::commit_elect(&bars[kFullRU]);
-                                TCP_T(long long q2 = clock64(); m_i += q2 - q1;)
-                                if (!dep) {
-                                    umma::mbar_wait(&bars[kCDone], cdw & 1);       // previous step's G_c has drained D_cx / D_ch
-                                    umma::fence_after_sync();
-                                }
-                                TCP_T(q1 = clock64(); m_w2 += q1 - q2;)
-                            }
-                            const bool xop = (e & 1) == 0, cand = e >= 2;
-                            const uint32_t dcol = tbase + (e < 2 ? kColRU : (e == 2 ? kColCX : kColCH));
-                            const uint32_t bh = cand ? (xop ? xc_hi : hc_hi) : (xop ? xru_hi : hru_hi);
-                            const uint32_t bl = cand ? (xop ? xc_lo : hc_lo) : (xop ? xru_lo : hru_lo);
-                            issue_part(dcol, xop ? rX : rH, bh, bl, xop && l == 0, cand ? idC : idRU, e == 1);
-                        }
-                        umma::commit_elect(&bars[kFullC]);
-                        TCP_T(m_i += clock64() - q1;)
+                        if (dep) umma::mbar_wait(&bars[kCDone], cdw & 1);          // previous step's state restaged
+                        umma::fence_after_sync();
+                        TCP_T(long long q2 = clock64(); m_w2 += q2 - q1;)
+                        issue_step(tbase, rX, rH, x_hi, x_lo, h_hi, h_lo, l == 0);
+                        umma::commit_elect(&bars[kFull]);
+                        TCP_T(m_i += clock64() - q2;)
                         ++g;
                         ++cdw;
                     }
@@ -651,9 +675,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
 
     if (warp == kMmaWarp) umma::tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        umma::mbar_init(&bars[kFullRU], 1);
-        umma::mbar_init(&bars[kFullC], 1);
-        umma::mbar_init(&bars[kRuFree], kRowThreads);
+        umma::mbar_init(&bars[kFull], 1);
+        umma::mbar_init(&bars[kAccFree], kRowThreads);
         umma::mbar_init(&bars[kCDone], kRowThreads);
         umma::mbar_init(&bars[kWImg], 1);
         umma::mbar_fence_init();
