@@ -89,6 +89,14 @@ int rnnwf_tfim_eloc(const rnnwf_model* m, const void* params, const uint8_t* sam
                     const double* jz, double bx, int flags, double* eloc_out, double* logp_out,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* As rnnwf_tfim_eloc, additionally returning the amplitude ratio of every single-flip configuration:
+ * ratios_out: double[ns * N], ratios_out[s * N + k] = psi(sigma_s with site k flipped) / psi(sigma_s) = exp((lp_{k+1} - lp_0) / 2), the
+ * terms the reference sums at 1DTFIM/TrainingRNN_1DTFIM.py:70-74 (2-D: slot order of Training2DRNN_2DTFIM.py:55-61).  Their
+ * sample mean is <sigma^x_k>: the per-site observable behind README.md:3 ("correlation functions").  Requires bx != 0.          */
+int rnnwf_tfim_flip_ratios(const rnnwf_model* m, const void* params, const uint8_t* samples, int64_t ns,
+                           const double* jz, double bx, int flags, double* eloc_out, double* logp_out, double* ratios_out,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* Which chain kernel rnnwf_tfim_eloc runs for `m`: 3 = tcgen05 kind::f16 with 3xFP16 operands, resident weights and the
  * MMA / gate-math software pipeline (FP32 probability-head GRU with 50 units, <= 3 layers), 2 = the same arithmetic without the
  * pipeline, 1 = tcgen05 kind::tf32 with 3xTF32 operands, 0 = CUDA-core FFMA tile engine (every other shape / dtype).  The

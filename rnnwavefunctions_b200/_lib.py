@@ -37,6 +37,7 @@ _SIGNATURES = {
     "rnnwf_sample": (C.c_int, [C.POINTER(Model), _P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P, C.c_size_t, _P]),
     "rnnwf_logpsi": (C.c_int, [C.POINTER(Model), _P, _P, C.c_int64, C.c_int, _P, _P, C.c_size_t, _P]),
     "rnnwf_tfim_eloc": (C.c_int, [C.POINTER(Model), _P, _P, C.c_int64, _P, C.c_double, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "rnnwf_tfim_flip_ratios": (C.c_int, [C.POINTER(Model), _P, _P, C.c_int64, _P, C.c_double, C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
     "rnnwf_tfim_chain_mode": (C.c_int, [C.POINTER(Model)]),
     "rnnwf_tfim_diag": (C.c_int, [C.POINTER(Model), _P, C.c_int64, _P, _P, _P]),
     "rnnwf_tfim_enumerate": (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),

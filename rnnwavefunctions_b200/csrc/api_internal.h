@@ -12,12 +12,12 @@ template <typename T> int gru_sample_t(const rnnwf_model& m, const void* params,
 template <typename T> int gru_logpsi_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, int flags,
                                        double* out, void* ws, size_t wsb, cudaStream_t s);
 template <typename T> int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns,
-                                          const double* jz, double bx, int flags, double* eloc, double* logp, void* ws,
-                                          size_t wsb, cudaStream_t s);
+                                          const double* jz, double bx, int flags, double* eloc, double* logp, double* ratios,
+                                          void* ws, size_t wsb, cudaStream_t s);
 int tfim_chain_mode_impl(const rnnwf_model& m);
 int tfim_diag_impl(const rnnwf_model& m, const uint8_t* samples, int64_t ns, const double* jz, double* diag, cudaStream_t s);
 int tfim_finalize_impl(const double* diag, const double* delta, const double* lp, int64_t ns, int N, int M, int tiles_s, double bx,
-                       int parity, double* eloc, double* logp, cudaStream_t s);
+                       int parity, double* eloc, double* logp, double* ratios, cudaStream_t s);
 int tfim_enumerate_impl(const uint8_t* samples, int64_t ns, int N, int32_t* queue, cudaStream_t s);
 
 // grad.cu
@@ -39,8 +39,8 @@ template <typename T> int mdrnn_sample_t(const rnnwf_model& m, const void* param
 template <typename T> int mdrnn_logpsi_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns,
                                          double* out, void* ws, size_t wsb, cudaStream_t s);
 template <typename T> int mdrnn_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns,
-                                            const double* jz, double bx, double* eloc, double* logp, void* ws, size_t wsb,
-                                            cudaStream_t s);
+                                            const double* jz, double bx, double* eloc, double* logp, double* ratios, void* ws,
+                                            size_t wsb, cudaStream_t s);
 template <typename T> int mdrnn_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns,
                                            const double* weights, double* grad, void* ws, size_t wsb, cudaStream_t s);
 

@@ -126,8 +126,21 @@ RNNWF_API int rnnwf_tfim_eloc(const rnnwf_model* m, const void* params, const ui
     if (int e = check_model(m)) return e;
     RNNWF_CHECK(params && samples && jz && eloc_out && ns > 0, -1, "bad arguments to rnnwf_tfim_eloc");
     cudaStream_t s = (cudaStream_t)stream;
-    if (m->cell == RNNWF_CELL_MDRNN) return DISPATCH(m, mdrnn_tfim_eloc_t, *m, params, samples, ns, jz, bx, eloc_out, logp_out, ws, ws_bytes, s);
-    return DISPATCH(m, gru_tfim_eloc_t, *m, params, samples, ns, jz, bx, flags, eloc_out, logp_out, ws, ws_bytes, s);
+    if (m->cell == RNNWF_CELL_MDRNN)
+        return DISPATCH(m, mdrnn_tfim_eloc_t, *m, params, samples, ns, jz, bx, eloc_out, logp_out, nullptr, ws, ws_bytes, s);
+    return DISPATCH(m, gru_tfim_eloc_t, *m, params, samples, ns, jz, bx, flags, eloc_out, logp_out, nullptr, ws, ws_bytes, s);
+}
+
+RNNWF_API int rnnwf_tfim_flip_ratios(const rnnwf_model* m, const void* params, const uint8_t* samples, int64_t ns, const double* jz,
+                           double bx, int flags, double* eloc_out, double* logp_out, double* ratios_out, void* ws, size_t ws_bytes,
+                           void* stream) {
+    if (int e = check_model(m)) return e;
+    RNNWF_CHECK(params && samples && jz && eloc_out && ratios_out && ns > 0, -1, "bad arguments to rnnwf_tfim_flip_ratios");
+    RNNWF_CHECK(bx != 0.0, -1, "rnnwf_tfim_flip_ratios: the single-flip chains are skipped when bx == 0 (as in the reference); pass bx != 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m->cell == RNNWF_CELL_MDRNN)
+        return DISPATCH(m, mdrnn_tfim_eloc_t, *m, params, samples, ns, jz, bx, eloc_out, logp_out, ratios_out, ws, ws_bytes, s);
+    return DISPATCH(m, gru_tfim_eloc_t, *m, params, samples, ns, jz, bx, flags, eloc_out, logp_out, ratios_out, ws, ws_bytes, s);
 }
 
 RNNWF_API int rnnwf_tfim_chain_mode(const rnnwf_model* m) {

@@ -89,7 +89,7 @@ __device__ __forceinline__ double logaddexp_(double a, double b) {
 // Parity model: P_sym = (P(s) + P(rev s))/2, the flip at site k appears at N-1-k in the reversed chain.
 __global__ void tfim_finalize_kernel(const double* __restrict__ diag, const double* __restrict__ delta,
                                      const double* __restrict__ lp, int64_t ns, int N, int M, int tiles_s, double bx,
-                                     int parity, double* __restrict__ eloc, double* __restrict__ logp) {
+                                     int parity, double* __restrict__ eloc, double* __restrict__ logp, double* __restrict__ ratios) {
     const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (b >= ns) return;
     const int64_t st = b / M;
@@ -99,7 +99,11 @@ __global__ void tfim_finalize_kernel(const double* __restrict__ diag, const doub
     if (!parity) {
         lpb = lp[st * M + m];
         if (bx != 0.0)
-            for (int k = 0; k < N; ++k) sum += exp(0.5 * delta[(st * N + k) * M + m]);
+            for (int k = 0; k < N; ++k) {
+                const double r = exp(0.5 * delta[(st * N + k) * M + m]);
+                sum += r;
+                if (ratios) ratios[b * N + k] = r;
+            }
     } else {
         const int64_t st2 = st + tiles_s;
         const double lp1 = lp[st * M + m], lp2 = lp[st2 * M + m];
@@ -108,7 +112,9 @@ __global__ void tfim_finalize_kernel(const double* __restrict__ diag, const doub
             for (int k = 0; k < N; ++k) {
                 const double a = lp1 + delta[(st * N + k) * M + m];
                 const double c = lp2 + delta[(st2 * N + (N - 1 - k)) * M + m];
-                sum += exp(0.5 * (logaddexp_(a, c) - ln2 - lpb));
+                const double r = exp(0.5 * (logaddexp_(a, c) - ln2 - lpb));
+                sum += r;
+                if (ratios) ratios[b * N + k] = r;
             }
     }
     eloc[b] = diag[b] - bx * sum;
@@ -151,6 +157,7 @@ template <typename T> struct GruWs {
     uint8_t* sigT;
     T* hstore;
     double *la_sel, *la_oth, *ph_sel, *ph_oth, *delta_re, *delta_im, *lp_re, *lp_im, *diag;
+    float* la_self;   // FP32 copy of la_sel for the pipelined tensor-core chains (keeps FP64 out of their site loop)
     int *counter, *order;
 };
 
@@ -169,6 +176,7 @@ static GruWs<T> carve_gru(Ws& ws, const GruLayout& g, const GruLaunch& c, int64_
         w.hstore = ws.take<T>(rows * g.N * g.L * g.H);
         w.la_sel = ws.take<double>(rows * g.N);
         w.la_oth = ws.take<double>(rows * g.N);
+        w.la_self = ws.take<float>(rows * g.N);
         if (cplx) {
             w.ph_sel = ws.take<double>(rows * g.N);
             w.ph_oth = ws.take<double>(rows * g.N);
@@ -356,7 +364,7 @@ template int gru_logpsi_t<double>(const rnnwf_model&, const void*, const uint8_t
 
 template <typename T>
 int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, const double* jz, double bx,
-                    int flags, double* eloc, double* logp, void* wsp, size_t wsb, cudaStream_t s) {
+                    int flags, double* eloc, double* logp, double* ratios, void* wsp, size_t wsb, cudaStream_t s) {
     const GruLayout g = make_gru_layout(m);
     const GruLaunch c = choose_gru_launch<T>(g);
     RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
@@ -377,7 +385,7 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     prof_count(); tfim_diag_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(samples, ns, g.N, m.nx, m.ny, jz, w.diag);
     if (mode == 3) {
         if constexpr (std::is_same<T, float>::value) {
-            if (int e = tc16p::launch_eloc(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.lp_re, w.delta_re,
+            if (int e = tc16p::launch_eloc(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.la_self, w.lp_re, w.delta_re,
                                            w.counter, bx != 0.0, s))
                 return e;
         }
@@ -398,14 +406,14 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     } else {
         if (int e = launch_forward<T, false, false>(g, c, w, tiles, s)) return e;
     }
-    prof_count(); tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(w.diag, w.delta_re, w.lp_re, ns, g.N, c.M, tiles_s, bx, parity, eloc, logp);
+    prof_count(); tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(w.diag, w.delta_re, w.lp_re, ns, g.N, c.M, tiles_s, bx, parity, eloc, logp, ratios);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }
 template int gru_tfim_eloc_t<float>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, double, int, double*,
-                                    double*, void*, size_t, cudaStream_t);
+                                    double*, double*, void*, size_t, cudaStream_t);
 template int gru_tfim_eloc_t<double>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, double, int, double*,
-                                     double*, void*, size_t, cudaStream_t);
+                                     double*, double*, void*, size_t, cudaStream_t);
 
 int tfim_chain_mode_impl(const rnnwf_model& m) {
     if (m.cell != RNNWF_CELL_GRU || m.dtype != RNNWF_F32 || m.head != RNNWF_HEAD_PROB) return 0;
@@ -419,8 +427,8 @@ int tfim_diag_impl(const rnnwf_model& m, const uint8_t* samples, int64_t ns, con
 }
 
 int tfim_finalize_impl(const double* diag, const double* delta, const double* lp, int64_t ns, int N, int M, int tiles_s, double bx,
-                       int parity, double* eloc, double* logp, cudaStream_t s) {
-    prof_count(); tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(diag, delta, lp, ns, N, M, tiles_s, bx, parity, eloc, logp);
+                       int parity, double* eloc, double* logp, double* ratios, cudaStream_t s) {
+    prof_count(); tfim_finalize_kernel<<<(int)cdiv(ns, 128), 128, 0, s>>>(diag, delta, lp, ns, N, M, tiles_s, bx, parity, eloc, logp, ratios);
     RNNWF_CUDA(cudaGetLastError());
     return 0;
 }

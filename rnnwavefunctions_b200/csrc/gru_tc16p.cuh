@@ -43,6 +43,9 @@
 #ifndef RNNWF_CAND
 #define RNNWF_CAND 0
 #endif
+#ifndef RNNWF_FUSED
+#define RNNWF_FUSED 0
+#endif
 
 namespace rnnwf {
 namespace tc16p {
@@ -52,6 +55,14 @@ using tc16::rcp;
 using tc16::pack_h2;
 using tc16::unpack_h2;
 using tc16::core_off;
+
+// packed FP32 pairs (FFMA2 / FADD2 on sm_100a): one issue slot for two lanes of the gate arithmetic
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_make(float a, float b) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_split(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) { f2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 constexpr int kRows = 128, kRowThreads = 256, kThreads = 384, kMmaWarp = 8;   // warps 9-11 only complete the MMA warp's warpgroup (setmaxnreg)
 constexpr int kUP = 25;                                  // units per row thread (H = 50, two threads per row)
@@ -175,7 +186,13 @@ template <int NC> __device__ __forceinline__ void stage_cols(uint32_t col, const
         const uint32_t wh = pack_h2(h[2 * c], h[2 * c + 1]);
         const float2 f = unpack_h2(wh);
         hi[c] = __uint_as_float(wh);
+#if RNNWF_CAND == 2
+        float d0, d1;
+        f2_split(f2_sub(f2_make(h[2 * c], h[2 * c + 1]), f2_make(f.x, f.y)), d0, d1);
+        lo[c] = __uint_as_float(pack_h2(d0, d1));
+#else
         lo[c] = __uint_as_float(pack_h2(h[2 * c] - f.x, h[2 * c + 1] - f.y));
+#endif
     }
     if constexpr (NC == 4) {
         umma::tmem_st4(col, hi);
@@ -202,7 +219,8 @@ struct Args {
     const unsigned char* img;
     const uint8_t* sigT;
     float* hstore;            // BASE: written (every layer, every site); FLIP: restart states
-    double *la_sel, *la_oth;  // BASE: written; FLIP: read
+    double *la_sel, *la_oth;  // BASE: written; FLIP: read (at the modified site only)
+    float* la_self;           // FP32 copy of la_sel (the values are FP32 numbers): what the flip chains subtract site by site
     double* lp;               // BASE: sum_n la_sel
     double* delta;            // FLIP: [tile][slot][M]
     int* counter;
@@ -228,6 +246,8 @@ struct Ctx {
     int psg, pn;
     uint32_t pph, pbuf;
     double p_la, p_ph;        // base-pass la_sel / ph_sel of the pending site (loaded a step ahead: global latency off the critical path)
+    float p_laf, accf, compf; // probability head: the site terms are FP32 numbers, summed with Kahan compensation in FP32 -- FP64
+                              // instructions in the site loop cost ~150 cycles each on this part (ncu: stall_math on every DADD)
     int nup;
     double acc, acc_im;
 #ifdef RNNWF_TC16P_DEBUG
@@ -296,6 +316,70 @@ template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(cons
     }
 }
 
+// probability head without FP64: log-softmax term of the pending top-layer step in FP32 (log1pf / expf, ~1e-7 relative, the same
+// numbers finish_head casts to double), accumulated with Kahan compensation.  FLIP: term - base term, both FP32 numbers of nearly
+// equal magnitude, so the difference is (almost always) exact.
+template <bool BASE> __device__ __forceinline__ void finish_head_f32(const Args& a, Ctx& c) {
+    if (c.pn < 0) return;
+    const int pn = c.pn, psg = c.psg;
+    c.pn = -1;
+    umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
+    if (!c.live) return;
+    const float4 o = c.zsm[c.pbuf * kRows + c.rowi];
+    const float f0 = c.pz.x + o.x + c.tab[128], f1 = c.pz.y + o.y + c.tab[129];
+    const float dsel = psg ? f0 - f1 : f1 - f0;                             // z_other - z_selected
+    const float ls = dsel > 30.f ? -dsel : -log1pf(expf(dsel));
+    float term = ls;
+    if (BASE) {
+        const float lo = -dsel > 30.f ? dsel : -log1pf(expf(-dsel));
+        const size_t o_ = (c.rowbase + pn) * a.Mold + c.m;
+        a.la_sel[o_] = (double)ls;
+        a.la_oth[o_] = (double)lo;
+        a.la_self[o_] = ls;
+    } else {
+        term = ls - c.p_laf;
+    }
+    const float y = term - c.compf, t = c.accf + y;
+    c.compf = (t - c.accf) - y;
+    c.accf = t;
+}
+
+// reset / update gates 1/(1 + 2^a) of two units, in place.  RNNWF_GATES selects how many reciprocals are shared (MUFU pipe against
+// issue slots): 0: r0, u0, r1, u1 share ONE reciprocal (exponents clamped to 30, so the product of the four denominators stays
+// below 2^121): 2.5 MUFU and 11 instructions per unit;  1: one reciprocal per gate (ex2(+big) = inf -> 1/inf = 0, no clamps): 4 MUFU,
+// 6 instructions;  2: r and u of a unit share a reciprocal: 3 MUFU, 10 instructions;  3: as 1 with packed additions
+__device__ __forceinline__ void ru_one(float& r, float& u) {
+#if RNNWF_GATES == 1 || RNNWF_GATES == 3
+    r = rcp(1.0f + ex2(r));
+    u = rcp(1.0f + ex2(u));
+#else
+    const float er = 1.0f + ex2(fminf(r, 60.f)), eu = 1.0f + ex2(fminf(u, 60.f));
+    const float inv = rcp(er * eu);
+    r = inv * eu; u = inv * er;
+#endif
+}
+__device__ __forceinline__ void ru_pair(float& r0, float& u0, float& r1, float& u1) {
+#if RNNWF_GATES == 0
+    const float er0 = 1.0f + ex2(fminf(r0, 30.f)), eu0 = 1.0f + ex2(fminf(u0, 30.f));
+    const float er1 = 1.0f + ex2(fminf(r1, 30.f)), eu1 = 1.0f + ex2(fminf(u1, 30.f));
+    const float p0 = er0 * eu0, p1 = er1 * eu1;
+    const float inv = rcp(p0 * p1);
+    const float i0 = inv * p1, i1 = inv * p0;                          // 1/p0, 1/p1
+    r0 = i0 * eu0; u0 = i0 * er0;
+    r1 = i1 * eu1; u1 = i1 * er1;
+#elif RNNWF_GATES == 3
+    const f2_t one2 = f2_make(1.0f, 1.0f);
+    float a0, a1;
+    f2_split(f2_add(f2_make(ex2(r0), ex2(r1)), one2), a0, a1);
+    r0 = rcp(a0); r1 = rcp(a1);
+    f2_split(f2_add(f2_make(ex2(u0), ex2(u1)), one2), a0, a1);
+    u0 = rcp(a0); u1 = rcp(a1);
+#else
+    ru_one(r0, u0);
+    ru_one(r1, u1);
+#endif
+}
+
 // one (site n, layer l) step of a row thread: pull the step's accumulators out of TMEM, release them to the MMA warp, then
 // reset / update gates, candidate, new state, head partial sums and restaging from registers.
 // hp: this thread's 25 units of h^l (previous site in, this site out).
@@ -310,11 +394,17 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
     // (n + 1, 0) / selected outcome of the head) and the base-pass terms of site n
     int spin_n = 0;
     double la_n = 0.0, ph_n = 0.0;
-    if (part == 0 && c.live && (l == 0 || top)) {
+    float la_nf = 0.f;
+    // (part 0 finishes the head, part 1 stages the one-hot input: the two warps of an SM sub-partition carry similar extra work)
+    if (c.live && ((part == 0 && top) || (part == 1 && l == 0))) {
         spin_n = spin_of<BASE>(a, c, n);
-        if (!BASE && top) {
-            la_n = a.la_sel[(c.rowbase + n) * Mold + c.m];
-            if (CPLX) ph_n = a.ph_sel[(c.rowbase + n) * Mold + c.m];
+        if (!BASE && top && part == 0) {
+            if (CPLX) {
+                la_n = a.la_sel[(c.rowbase + n) * Mold + c.m];
+                ph_n = a.ph_sel[(c.rowbase + n) * Mold + c.m];
+            } else {
+                la_nf = a.la_self[(c.rowbase + n) * Mold + c.m];
+            }
         }
     }
     TCP_T(long long t0 = clock64();)
@@ -340,40 +430,18 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
     umma::fence_before_sync();
     umma::mbar_arrive(&c.bars[kAccFree]);              // the accumulators may be overwritten by the next step's MMAs
     TCP_T(long long t2 = clock64(); c.w_c += t2 - t1;)
-    if (part == 0) finish_head<BASE, CPLX>(a, c);
-    // ---- reset / update gates 1/(1 + 2^a).  RNNWF_GATES selects how many reciprocals are shared (MUFU pipe against issue slots):
-    // 0: r0, u0, r1, u1 of two units share ONE reciprocal (exponents clamped to 30, so the product of the four denominators stays
-    //    below 2^121): 2.5 MUFU and 11 instructions per unit;  1: one reciprocal per gate (ex2(+big) = inf -> 1/inf = 0, no clamps):
-    //    4 MUFU, 6 instructions;  2: r and u of a unit share a reciprocal: 3 MUFU, 10 instructions
-#if RNNWF_GATES == 0
+    if (part == 0) {
+        if constexpr (CPLX) finish_head<BASE, CPLX>(a, c);
+        else finish_head_f32<BASE>(a, c);
+    }
+    // ---- reset / update gates (see ru_pair).  RNNWF_FUSED: the gates of a unit pair are computed right before its candidate, so
+    // that the MUFU-heavy head of one pair and the MUFU-free tail (state update, FP16 split, restaging) of the previous ones sit in
+    // the same scheduling window: both warps of an SM sub-partition run the same phase at the same time, and a phase that is all
+    // ex2 / rcp is bound by the 4-lane XU pipe while the issue slots idle
+#if !RNNWF_FUSED
 #pragma unroll
-    for (int q = 0; q < kUP - 1; q += 2) {
-        const float er0 = 1.0f + ex2(fminf(rr[q], 30.f)), eu0 = 1.0f + ex2(fminf(uu[q], 30.f));
-        const float er1 = 1.0f + ex2(fminf(rr[q + 1], 30.f)), eu1 = 1.0f + ex2(fminf(uu[q + 1], 30.f));
-        const float p0 = er0 * eu0, p1 = er1 * eu1;
-        const float inv = rcp(p0 * p1);
-        const float i0 = inv * p1, i1 = inv * p0;                          // 1/p0, 1/p1
-        rr[q] = i0 * eu0; uu[q] = i0 * er0;
-        rr[q + 1] = i1 * eu1; uu[q + 1] = i1 * er1;
-    }
-    {
-        const float er = 1.0f + ex2(fminf(rr[kUP - 1], 30.f)), eu = 1.0f + ex2(fminf(uu[kUP - 1], 30.f));
-        const float inv = rcp(er * eu);
-        rr[kUP - 1] = inv * eu; uu[kUP - 1] = inv * er;
-    }
-#elif RNNWF_GATES == 1
-#pragma unroll
-    for (int q = 0; q < kUP; ++q) {
-        rr[q] = rcp(1.0f + ex2(rr[q]));
-        uu[q] = rcp(1.0f + ex2(uu[q]));
-    }
-#else
-#pragma unroll
-    for (int q = 0; q < kUP; ++q) {
-        const float er = 1.0f + ex2(fminf(rr[q], 60.f)), eu = 1.0f + ex2(fminf(uu[q], 60.f));
-        const float inv = rcp(er * eu);
-        rr[q] = inv * eu; uu[q] = inv * er;
-    }
+    for (int q = 0; q < kUP - 1; q += 2) ru_pair(rr[q], uu[q], rr[q + 1], uu[q + 1]);
+    ru_one(rr[kUP - 1], uu[kUP - 1]);
 #endif
     TCP_T(long long t3 = clock64(); c.t_ru += t3 - t2;)
     // ---- candidate, new state, head partial sums, restaging
@@ -386,17 +454,28 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
 #pragma unroll
         for (int q = 0; q < 8; q += 2) {
             const int jl = 8 * gq + q;
+#if RNNWF_FUSED
+            ru_pair(rr[jl], uu[jl], rr[jl + 1], uu[jl + 1]);
+#endif
             // candidate tanh(x) = 1 - 2 / (1 + 2^a), a = 2 log2(e) x.  RNNWF_CAND 0: two units share a reciprocal, 1: one each
 #if RNNWF_CAND == 0
             const float ec0 = 1.0f + ex2(fminf(fmaf(rr[jl], dq[jl], dc[jl]), 60.f));
             const float ec1 = 1.0f + ex2(fminf(fmaf(rr[jl + 1], dq[jl + 1], dc[jl + 1]), 60.f));
             const float ic = rcp(ec0 * ec1);
             const float c0 = fmaf(-2.0f, ic * ec1, 1.0f), c1 = fmaf(-2.0f, ic * ec0, 1.0f);
-#else
+#elif RNNWF_CAND == 1
             const float c0 = fmaf(-2.0f, rcp(1.0f + ex2(fmaf(rr[jl], dq[jl], dc[jl]))), 1.0f);
             const float c1 = fmaf(-2.0f, rcp(1.0f + ex2(fmaf(rr[jl + 1], dq[jl + 1], dc[jl + 1]))), 1.0f);
 #endif
+#if RNNWF_CAND != 2
             const float h0 = fmaf(uu[jl], hp[jl] - c0, c0), h1 = fmaf(uu[jl + 1], hp[jl + 1] - c1, c1);
+#else       // packed: pre-activation, 1 + 2^a, 1 - 2/(.), h - c and the state update are one instruction per unit pair each
+            float a0, a1, h0, h1;
+            f2_split(f2_fma(f2_make(rr[jl], rr[jl + 1]), f2_make(dq[jl], dq[jl + 1]), f2_make(dc[jl], dc[jl + 1])), a0, a1);
+            f2_split(f2_add(f2_make(ex2(a0), ex2(a1)), f2_make(1.0f, 1.0f)), a0, a1);
+            const f2_t cc = f2_fma(f2_make(-2.0f, -2.0f), f2_make(rcp(a0), rcp(a1)), f2_make(1.0f, 1.0f));
+            f2_split(f2_fma(f2_make(uu[jl], uu[jl + 1]), f2_sub(f2_make(hp[jl], hp[jl + 1]), cc), cc), h0, h1);
+#endif
             hp[jl] = h0;
             hp[jl + 1] = h1;
             if (top) {
@@ -421,6 +500,9 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
     }
     {   // unit 24 of this half, staged next to this half's share of the constant-1 column
         const int jl = kUP - 1;
+#if RNNWF_FUSED
+        ru_one(rr[jl], uu[jl]);
+#endif
         const float ec = 1.0f + ex2(fminf(fmaf(rr[jl], dq[jl], dc[jl]), 60.f));
         const float cc = fmaf(-2.0f, rcp(ec), 1.0f);
         const float h0 = fmaf(uu[jl], hp[jl] - cc, cc);
@@ -437,7 +519,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
         const float tail[2] = {h0, part == 0 ? 1.0f : 0.0f};
         stage_cols<1>(reg + 12, tail);
     }
-    if (part == 0 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
+    if (part == 1 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
         const int code = c.live ? spin_n : 2;
         const float oh[1] = {__uint_as_float(pack_h2(code == 0 ? 1.f : 0.f, code == 1 ? 1.f : 0.f))};
         umma::tmem_st1(c.lane_addr + kColR + 64 * L, oh);
@@ -449,6 +531,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, fl
             c.psg = spin_n;
             c.p_la = la_n;
             c.p_ph = ph_n;
+            c.p_laf = la_nf;
             c.pph = c.cda;
             c.pbuf = par;
         } else {
@@ -519,7 +602,13 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
         }
     }
     asm volatile("bar.sync 2, %0;" ::"n"(kRowThreads) : "memory");   // part 1's partials of the last site
-    if (part == 0) finish_head<BASE, CPLX>(a, c);
+    if (part == 0) {
+        if constexpr (CPLX) finish_head<BASE, CPLX>(a, c);
+        else {
+            finish_head_f32<BASE>(a, c);
+            c.acc += (double)c.accf - (double)c.compf;
+        }
+    }
 }
 
 // the MMA instructions of one (site, layer) step; executed by every lane of the (converged) MMA warp, one elected lane issues.
@@ -605,7 +694,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
                 Ctx c;
                 c.tab = tab; c.zsm = zsm; c.bars = bars; c.lane_addr = lane_addr; c.rowi = rowi; c.m = m; c.part = part; c.live = live;
                 c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.acc = acc; c.acc_im = acc_im;
-                c.pz = make_float4(0.f, 0.f, 0.f, 0.f); c.psg = 0; c.pn = -1; c.pph = 0; c.pbuf = 0; c.nup = 0; c.p_la = 0.0; c.p_ph = 0.0;
+                c.pz = make_float4(0.f, 0.f, 0.f, 0.f); c.psg = 0; c.pn = -1; c.pph = 0; c.pbuf = 0; c.nup = 0; c.p_la = 0.0; c.p_ph = 0.0; c.p_laf = 0.f; c.accf = 0.f; c.compf = 0.f;
                 TCP_T(c.w_ru = c.w_c = c.t_ru = c.t_c = 0; long long ch0 = clock64();)
                 row_chain<BASE, CPLX>(a, c);
                 acc = c.acc; acc_im = c.acc_im;
@@ -757,7 +846,7 @@ static int launch_chains(Args& a, int sms, bool flips, cudaStream_t s) {
 }
 
 static Args make_args(const GruLayout& g, int Mold, int tiles, unsigned char* img, const uint8_t* sigT, float* hstore, double* la_sel,
-                      double* la_oth, double* lp, double* delta, int* counter, int& sms) {
+                      double* la_oth, float* la_self, double* lp, double* delta, int* counter, int& sms) {
     int dev = 0;
     sms = 148;
     cudaGetDevice(&dev);
@@ -767,16 +856,16 @@ static Args make_args(const GruLayout& g, int Mold, int tiles, unsigned char* im
     a.g = g; a.t = make_layout(g); a.Mold = Mold;
     a.rows_total = (int64_t)tiles * Mold;
     a.tiles128 = (int)cdiv(a.rows_total, kRows);
-    a.img = img; a.sigT = sigT; a.hstore = hstore; a.la_sel = la_sel; a.la_oth = la_oth; a.lp = lp; a.delta = delta; a.counter = counter;
+    a.img = img; a.sigT = sigT; a.hstore = hstore; a.la_sel = la_sel; a.la_oth = la_oth; a.la_self = la_self; a.lp = lp; a.delta = delta; a.counter = counter;
     a.nslots = g.N;
     return a;
 }
 
 // base pass + single-flip chains (FP32 pRNN with 50 units)
 static int launch_eloc(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
-                       double* la_sel, double* la_oth, double* lp, double* delta, int* counter, bool flips, cudaStream_t s) {
+                       double* la_sel, double* la_oth, float* la_self, double* lp, double* delta, int* counter, bool flips, cudaStream_t s) {
     int sms;
-    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, lp, delta, counter, sms);
+    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, la_self, lp, delta, counter, sms);
     prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);
     return launch_chains<false>(a, sms, flips, s);
 }
@@ -786,7 +875,7 @@ static int launch_j1j2(const GruLayout& g, int Mold, int tiles, const float* par
                        double* la_sel, double* la_oth, double* ph_sel, double* ph_oth, double* lp_re, double* lp_im, double* delta_re,
                        double* delta_im, const int* order, const double* j1, const double* j2, int* counter, cudaStream_t s) {
     int sms;
-    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, lp_re, delta_re, counter, sms);
+    Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, nullptr, lp_re, delta_re, counter, sms);
     a.ph_sel = ph_sel; a.ph_oth = ph_oth; a.lp_im = lp_im; a.delta_im = delta_im; a.order = order; a.j1 = j1; a.j2 = j2;
     a.n_kind1 = g.N - 1; a.n_kind2 = g.N - 2; a.nslots = a.n_kind1 + a.n_kind2;
     prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);

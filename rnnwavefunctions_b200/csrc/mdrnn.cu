@@ -699,7 +699,7 @@ template int mdrnn_logpsi_t<double>(const rnnwf_model&, const void*, const uint8
 
 template <typename T>
 int mdrnn_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, const double* jz, double bx,
-                      double* eloc, double* logp, void* wsp, size_t wsb, cudaStream_t s) {
+                      double* eloc, double* logp, double* ratios, void* wsp, size_t wsb, cudaStream_t s) {
     const MdLayout g = make_md_layout(m);
     const MdLaunch c = md_launch_for<T>(g, RNNWF_OP_TFIM_ELOC);
     if (int e = md_check<T>(m, c)) return e;
@@ -728,12 +728,12 @@ int mdrnn_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* s
         prof_mark(1, s);
         RNNWF_CUDA(cudaGetLastError());
     }
-    return tfim_finalize_impl(w.diag, w.delta, w.lp, ns, g.N, c.M, tiles, bx, 0, eloc, logp, s);
+    return tfim_finalize_impl(w.diag, w.delta, w.lp, ns, g.N, c.M, tiles, bx, 0, eloc, logp, ratios, s);
 }
 template int mdrnn_tfim_eloc_t<float>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, double, double*,
-                                      double*, void*, size_t, cudaStream_t);
+                                      double*, double*, void*, size_t, cudaStream_t);
 template int mdrnn_tfim_eloc_t<double>(const rnnwf_model&, const void*, const uint8_t*, int64_t, const double*, double, double*,
-                                       double*, void*, size_t, cudaStream_t);
+                                       double*, double*, void*, size_t, cudaStream_t);
 
 template <typename T>
 static int md_launch_wgrad(const MdLayout& g, const MdWs<T>& w, const uint8_t* samples, int64_t ns, int M, int64_t nblk, bool head,

@@ -116,6 +116,20 @@ def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
     return eloc, logp
 
 
+def tfim_flip_ratios(model, params, samples_u8, jz, bx, flags=0):
+    """-> (eloc [ns], logp [ns], ratios [ns, N]) with ratios[s, k] = psi(sigma_s, site k flipped) / psi(sigma_s) (rnnwf_tfim_flip_ratios)."""
+    _check_params(model, params)
+    ns = samples_u8.shape[0]
+    ws, nb = _ws_for(model, OP_TFIM_ELOC, ns, flags, params.device)
+    jz = torch.as_tensor(jz, dtype=torch.float64).reshape(-1).to(params.device).contiguous()
+    eloc = torch.empty(ns, dtype=torch.float64, device=params.device)
+    logp = torch.empty(ns, dtype=torch.float64, device=params.device)
+    ratios = torch.empty((ns, model.n_sites), dtype=torch.float64, device=params.device)
+    check(_lib.load().rnnwf_tfim_flip_ratios(C.byref(model), _ptr(params), _ptr(samples_u8), ns, _ptr(jz), float(bx), flags, _ptr(eloc),
+                                             _ptr(logp), _ptr(ratios), _ptr(ws), nb, _stream()))
+    return eloc, logp, ratios
+
+
 def tfim_chain_mode(model) -> int:
     """3: pipelined tcgen05 3xFP16 chain kernel, 2: unpipelined 3xFP16, 1: tcgen05 3xTF32, 0: CUDA-core FFMA (see include/rnnwf.h)."""
     return int(_lib.load().rnnwf_tfim_chain_mode(C.byref(model)))

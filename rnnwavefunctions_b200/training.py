@@ -123,6 +123,22 @@ def _print_params(wf, verbose):
     return total
 
 
+def _schedule(lr, lr_schedule):
+    """Learning-rate schedules the reference ships: constant (1DTFIM/TrainingRNN_1DTFIM.py:221,
+    J1J2/TrainingRNN_J1J2.py:304), 'inverse' = 1/((1/lr) + it/10) (2DTFIM_1DRNN/Training1DRNN_2DTFIM.py:229 and the
+    commented alternative at J1J2/TrainingRNN_J1J2.py:301-302), 'inverse5000' = lr (1 + it/5000)^-1
+    (2DTFIM_2DRNN/Training2DRNN_2DTFIM.py:228); or any callable it -> lr."""
+    if callable(lr_schedule):
+        return lr_schedule
+    if lr_schedule in (None, "constant"):
+        return lambda it: lr
+    if lr_schedule == "inverse":
+        return lambda it: 1.0 / ((1.0 / lr) + it / 10.0)
+    if lr_schedule == "inverse5000":
+        return lambda it: lr * (1.0 + it / 5000.0) ** -1
+    raise ValueError(f"unknown lr_schedule {lr_schedule!r}")
+
+
 def _units_ending(units):
     return "_units" + "".join("_{0}".format(u) for u in units)
 
@@ -163,7 +179,7 @@ def _run(wf, hamiltonian, numsteps, numsamples, lr_of_it, numsamples_tag, save_p
 
 def run_1DTFIM(numsteps=10 ** 4, systemsize=20, num_units=50, Bx=1, num_layers=1, numsamples=500, learningrate=5e-3, seed=111, *,
                parity_symmetric=False, save=True, checkpoint_dir="../Check_Points/1DTFIM", verbose=True, resume=False,
-               device=None):
+               device=None, lr_schedule=None):
     """VMC of the open 1-D TFIM with a stacked-GRU pRNN (1DTFIM/TrainingRNN_1DTFIM.py:79-229).
     Returns (meanEnergy, varEnergy): lists of length numsteps+1; entry `it` belongs to the parameters before
     update `it`.  `parity_symmetric` selects RNNwavefunction_paritysym (the reference swaps an import, :9-10).
@@ -178,7 +194,7 @@ def run_1DTFIM(numsteps=10 ** 4, systemsize=20, num_units=50, Bx=1, num_layers=1
     _print_params(wf, verbose)
     ending = _units_ending(units)
     tag = "_N" + str(N) + "_samp" + str(numsamples) + "_Jz" + str(Jz[0]) + "_Bx" + str(Bx) + "_GRURNN_OBC" + "_TFIM" + ending
-    return _run(wf, TFIM(Jz, Bx), numsteps, numsamples, lambda it: lr, numsamples, checkpoint_dir,
+    return _run(wf, TFIM(Jz, Bx), numsteps, numsamples, _schedule(lr, lr_schedule), numsamples, checkpoint_dir,
                 "meanEnergy" + tag + ".npy", "varEnergy" + tag + ".npy",
                 "RNNwavefunction_N" + str(N) + "_samp" + str(numsamples) + "_Jz1Bx" + str(Bx) + "_GRURNN_OBC" + ending + ".npz",
                 save, verbose, resume)
@@ -186,7 +202,7 @@ def run_1DTFIM(numsteps=10 ** 4, systemsize=20, num_units=50, Bx=1, num_layers=1
 
 def run_2DTFIM_1DRNN(numsteps=2 * 10 ** 4, systemsize_x=5, systemsize_y=5, Bx=+2, num_units=50, num_layers=1, numsamples=500,
                      learningrate=1e-3, seed=333, *, save=True, checkpoint_dir="../Check_Points/2DTFIM", verbose=True,
-                     resume=False, device=None):
+                     resume=False, device=None, lr_schedule="inverse"):
     """2-D TFIM with a 1-D GRU pRNN over the flattened lattice, float64
     (2DTFIM_1DRNN/Training1DRNN_2DTFIM.py:85-233); lr schedule 1/((1/lr)+it/10) (:229)."""
     _seed_everything(seed)
@@ -198,14 +214,14 @@ def run_2DTFIM_1DRNN(numsteps=2 * 10 ** 4, systemsize_x=5, systemsize_y=5, Bx=+2
     _print_params(wf, verbose)
     ending = _units_ending(units)[1:]    # the 2-D apps spell it 'units_50' (:137-139)
     tag = "_" + str(Nx) + "x" + str(Ny) + "_Bx" + str(Bx) + "_lradap" + str(lr) + "_samp" + str(numsamples) + ending
-    return _run(wf, TFIM(Jz, Bx), numsteps, numsamples, lambda it: 1.0 / ((1.0 / lr) + it / 10.0), numsamples, checkpoint_dir,
+    return _run(wf, TFIM(Jz, Bx), numsteps, numsamples, _schedule(lr, lr_schedule), numsamples, checkpoint_dir,
                 "meanEnergy_GRURNN" + tag + "_2DTFIM.npy", "varEnergy_GRURNN" + tag + "_2DTFIM.npy",
                 "RNNwavefunction_GRURNN" + tag + ".npz", save, verbose, resume)
 
 
 def run_2DTFIM_2DRNN(numsteps=2 * 10 ** 4, systemsize_x=5, systemsize_y=5, Bx=+2, num_units=50, numsamples=500,
                      learningrate=5e-3, seed=111, *, save=True, checkpoint_dir="../Check_Points/2DTFIM", verbose=True,
-                     resume=False, device=None):
+                     resume=False, device=None, lr_schedule="inverse5000"):
     """2-D TFIM with the 2-D RNN (MDRNNcell on the zig-zag path), float64
     (2DTFIM_2DRNN/Training2DRNN_2DTFIM.py:88-231); lr schedule lr (1+it/5000)^-1 (:228).
     (As shipped the reference raises UnboundLocalError at :99; this is the intended function.)"""
@@ -218,14 +234,14 @@ def run_2DTFIM_2DRNN(numsteps=2 * 10 ** 4, systemsize_x=5, systemsize_y=5, Bx=+2
     _print_params(wf, verbose)
     ending = _units_ending(units)[1:]
     tag = "_" + str(Nx) + "x" + str(Ny) + "_Bx" + str(Bx) + "_lradap" + str(lr) + "_samp" + str(numsamples) + ending
-    return _run(wf, TFIM(Jz, Bx), numsteps, numsamples, lambda it: lr * (1.0 + it / 5000.0) ** -1, numsamples, checkpoint_dir,
+    return _run(wf, TFIM(Jz, Bx), numsteps, numsamples, _schedule(lr, lr_schedule), numsamples, checkpoint_dir,
                 "meanEnergy_2DVanillaRNN" + tag + "_2DTFIM.npy", "varEnergy_2DVanillaRNN" + tag + "_2DTFIM.npy",
                 "RNNwavefunction_2DVanillaRNN" + tag + ".npz", save, verbose, resume)
 
 
 def run_J1J2(numsteps=10 ** 5, systemsize=20, J1_=1.0, J2_=0.0, Marshall_sign=False, num_units=50, num_layers=1, numsamples=500,
              learningrate=2.5e-4, seed=111, *, reference_compat=False, save=True, checkpoint_dir="../Check_Points/J1J2",
-             verbose=True, resume=False, device=None):
+             verbose=True, resume=False, device=None, lr_schedule=None):
     """VMC of the open J1-J2 chain with the complex cRNN in the zero-magnetisation sector
     (J1J2/TrainingRNN_J1J2.py:131-308).  Returns (meanEnergy [complex], varEnergy [variance of the real part]).
     `Marshall_sign` applies the intended Marshall rotation; `reference_compat=True` reproduces the reference's
@@ -242,6 +258,6 @@ def run_J1J2(numsteps=10 ** 5, systemsize=20, J1_=1.0, J2_=0.0, Marshall_sign=Fa
     _print_params(wf, verbose)
     ending = _units_ending(units)
     tag = "_N" + str(N) + "_samp" + str(numsamples) + "_lradap" + str(lr) + "_complexGRURNN" + "_J1J2" + str(J2[0]) + ending   # :182-188
-    return _run(wf, J1J2(J1, J2, Bz, Marshall_sign), numsteps, numsamples, lambda it: lr, numsamples, checkpoint_dir,
+    return _run(wf, J1J2(J1, J2, Bz, Marshall_sign), numsteps, numsamples, _schedule(lr, lr_schedule), numsamples, checkpoint_dir,
                 "meanEnergy" + tag + "_zeromag.npy", "varEnergy" + tag + "_zeromag.npy", "RNNwavefunction" + tag + "_zeromag.npz",
                 save, verbose, resume, complex_energy=True)
