@@ -41,10 +41,13 @@
 #define RNNWF_GATES 0
 #endif
 #ifndef RNNWF_CAND
-#define RNNWF_CAND 0
+#define RNNWF_CAND 2
 #endif
 #ifndef RNNWF_FUSED
 #define RNNWF_FUSED 0
+#endif
+#ifndef RNNWF_UNROLL3
+#define RNNWF_UNROLL3 1
 #endif
 
 namespace rnnwf {
@@ -383,10 +386,11 @@ __device__ __forceinline__ void ru_pair(float& r0, float& u0, float& r1, float& 
 // one (site n, layer l) step of a row thread: pull the step's accumulators out of TMEM, release them to the MMA warp, then
 // reset / update gates, candidate, new state, head partial sums and restaging from registers.
 // hp: this thread's 25 units of h^l (previous site in, this site out).
-template <bool BASE, bool CPLX>
-__device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l, float* hp) {
+template <bool BASE, bool CPLX, int LS = -1>
+__device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn, float* hp) {
     constexpr int H = 50;
-    const int L = a.g.L, N = a.g.N, Mold = a.Mold, part = c.part;
+    const int L = LS >= 0 ? 3 : a.g.L, l = LS >= 0 ? LS : l_dyn;      // LS >= 0: the statically specialised copies of a 3-layer stack
+    const int N = a.g.N, Mold = a.Mold, part = c.part;
     const bool top = l == L - 1;
     const uint32_t par = c.g & 1;
     const uint32_t dpart = c.lane_addr + 28 * part;                       // this thread's columns inside a gate block
@@ -586,6 +590,16 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
     umma::mbar_arrive(&c.bars[kCDone]);                // "step -1": operands staged
     ++c.cda;
     const int n0 = s + 1;
+#if RNNWF_UNROLL3
+    if (L == 3) {   // one specialised copy of the step per layer: no register rotation, head / one-hot code only where it runs
+#pragma unroll 1
+        for (int d = n0; d <= N + 1; ++d) {
+            if (d - 2 >= n0 && d - 2 < N) row_step<BASE, CPLX, 2>(a, c, d - 2, 2, hA);
+            if (d - 1 >= n0 && d - 1 < N) row_step<BASE, CPLX, 1>(a, c, d - 1, 1, hB);
+            if (d < N) row_step<BASE, CPLX, 0>(a, c, d, 0, hC);
+        }
+    } else
+#endif
 #pragma unroll 1
     for (int d = n0; d <= N - 1 + L - 1; ++d) {        // anti-diagonals, top layer first
 #pragma unroll 1
