@@ -65,6 +65,17 @@ __device__ __forceinline__ f2_t f2_make(float a, float b) { f2_t r; asm("mov.b64
 __device__ __forceinline__ void f2_split(f2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) { f2_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// (-1/a, -1/b) on the FMA pipe: integer first guess (5 % off) + three Newton steps y <- y + y (1 + x y) in packed FP32 (1 ulp, as
+// MUFU.RCP).  8 issue slots instead of two trips through the 4-lane XU pipe; callers absorb the sign.  a, b in [1, 2^126).
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c);
+__device__ __forceinline__ f2_t f2_make(float a, float b);
+__device__ __forceinline__ f2_t neg_rcp2(float a, float b) {
+    const f2_t x = f2_make(a, b), one2 = f2_make(1.0f, 1.0f);
+    f2_t y = f2_make(__uint_as_float(0xFEF311C7u - __float_as_uint(a)), __uint_as_float(0xFEF311C7u - __float_as_uint(b)));
+#pragma unroll
+    for (int it = 0; it < 3; ++it) y = f2_fma(y, f2_fma(x, y, one2), y);
+    return y;
+}
 __device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 constexpr int kRows = 128, kRowThreads = 256, kThreads = 384, kMmaWarp = 8;   // warps 9-11 only complete the MMA warp's warpgroup (setmaxnreg)
@@ -189,7 +200,7 @@ template <int NC> __device__ __forceinline__ void stage_cols(uint32_t col, const
         const uint32_t wh = pack_h2(h[2 * c], h[2 * c + 1]);
         const float2 f = unpack_h2(wh);
         hi[c] = __uint_as_float(wh);
-#if RNNWF_CAND == 2
+#if RNNWF_CAND >= 2
         float d0, d1;
         f2_split(f2_sub(f2_make(h[2 * c], h[2 * c + 1]), f2_make(f.x, f.y)), d0, d1);
         lo[c] = __uint_as_float(pack_h2(d0, d1));
@@ -401,7 +412,8 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     float la_nf = 0.f;
     // (part 0 finishes the head, part 1 stages the one-hot input: the two warps of an SM sub-partition carry similar extra work)
     if (c.live && ((part == 0 && top) || (part == 1 && l == 0))) {
-        spin_n = spin_of<BASE>(a, c, n);
+        spin_n = a.sigT[(c.rowbase + n) * Mold + c.m];   // raw: the flip of a modified site is applied where the value is used, after
+                                                         // the gate math -- nothing before the accumulator drain may wait on this load
         if (!BASE && top && part == 0) {
             if (CPLX) {
                 la_n = a.la_sel[(c.rowbase + n) * Mold + c.m];
@@ -452,7 +464,8 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     const uint32_t reg = c.lane_addr + kColR + 64 * l + 16 * part;
     const float* tab = c.tab + 2 * kUP * part;
     float* hst = BASE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kUP * part) * Mold + c.m : nullptr;
-    float z0 = 0.f, z1 = 0.f, y0 = 0.f, y1 = 0.f;
+    float y0 = 0.f, y1 = 0.f;
+    f2_t z01 = f2_make(0.f, 0.f);                      // head partial sums (z0, z1), one packed FMA per unit
 #pragma unroll
     for (int gq = 0; gq < 3; ++gq) {
 #pragma unroll
@@ -471,22 +484,30 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
             const float c0 = fmaf(-2.0f, rcp(1.0f + ex2(fmaf(rr[jl], dq[jl], dc[jl]))), 1.0f);
             const float c1 = fmaf(-2.0f, rcp(1.0f + ex2(fmaf(rr[jl + 1], dq[jl + 1], dc[jl + 1]))), 1.0f);
 #endif
-#if RNNWF_CAND != 2
+#if RNNWF_CAND < 2
             const float h0 = fmaf(uu[jl], hp[jl] - c0, c0), h1 = fmaf(uu[jl + 1], hp[jl + 1] - c1, c1);
 #else       // packed: pre-activation, 1 + 2^a, 1 - 2/(.), h - c and the state update are one instruction per unit pair each
             float a0, a1, h0, h1;
             f2_split(f2_fma(f2_make(rr[jl], rr[jl + 1]), f2_make(dq[jl], dq[jl + 1]), f2_make(dc[jl], dc[jl + 1])), a0, a1);
+#if RNNWF_CAND == 2
             f2_split(f2_add(f2_make(ex2(a0), ex2(a1)), f2_make(1.0f, 1.0f)), a0, a1);
             const f2_t cc = f2_fma(f2_make(-2.0f, -2.0f), f2_make(rcp(a0), rcp(a1)), f2_make(1.0f, 1.0f));
+#elif RNNWF_CAND == 3   // the reciprocals on the FMA pipe
+            f2_split(f2_add(f2_make(ex2(fminf(a0, 60.f)), ex2(fminf(a1, 60.f))), f2_make(1.0f, 1.0f)), a0, a1);
+            const f2_t cc = f2_fma(f2_make(2.0f, 2.0f), neg_rcp2(a0, a1), f2_make(1.0f, 1.0f));
+#else                   // 4: one MUFU reciprocal for the two units
+            f2_split(f2_add(f2_make(ex2(fminf(a0, 60.f)), ex2(fminf(a1, 60.f))), f2_make(1.0f, 1.0f)), a0, a1);
+            const float ic = rcp(a0 * a1);
+            const f2_t cc = f2_fma(f2_make(-2.0f, -2.0f), f2_make(ic * a1, ic * a0), f2_make(1.0f, 1.0f));
+#endif
             f2_split(f2_fma(f2_make(uu[jl], uu[jl + 1]), f2_sub(f2_make(hp[jl], hp[jl + 1]), cc), cc), h0, h1);
 #endif
             hp[jl] = h0;
             hp[jl + 1] = h1;
             if (top) {
-                z0 = fmaf(h0, tab[2 * jl], z0);
-                z1 = fmaf(h0, tab[2 * jl + 1], z1);
-                z0 = fmaf(h1, tab[2 * jl + 2], z0);
-                z1 = fmaf(h1, tab[2 * jl + 3], z1);
+                const float2 w0 = *reinterpret_cast<const float2*>(tab + 2 * jl), w1 = *reinterpret_cast<const float2*>(tab + 2 * jl + 2);
+                z01 = f2_fma(f2_make(h0, h0), f2_make(w0.x, w0.y), z01);
+                z01 = f2_fma(f2_make(h1, h1), f2_make(w1.x, w1.y), z01);
                 if (CPLX) {
                     y0 = fmaf(h0, tab[132 + 2 * jl], y0);
                     y1 = fmaf(h0, tab[132 + 2 * jl + 1], y1);
@@ -512,8 +533,8 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
         const float h0 = fmaf(uu[jl], hp[jl] - cc, cc);
         hp[jl] = h0;
         if (top) {
-            z0 = fmaf(h0, tab[2 * jl], z0);
-            z1 = fmaf(h0, tab[2 * jl + 1], z1);
+            const float2 w0 = *reinterpret_cast<const float2*>(tab + 2 * jl);
+            z01 = f2_fma(f2_make(h0, h0), f2_make(w0.x, w0.y), z01);
             if (CPLX) {
                 y0 = fmaf(h0, tab[132 + 2 * jl], y0);
                 y1 = fmaf(h0, tab[132 + 2 * jl + 1], y1);
@@ -523,12 +544,15 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
         const float tail[2] = {h0, part == 0 ? 1.0f : 0.0f};
         stage_cols<1>(reg + 12, tail);
     }
+    if (!BASE && (n == c.s || n == c.t)) spin_n = 1 - spin_n;
     if (part == 1 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
         const int code = c.live ? spin_n : 2;
         const float oh[1] = {__uint_as_float(pack_h2(code == 0 ? 1.f : 0.f, code == 1 ? 1.f : 0.f))};
         umma::tmem_st1(c.lane_addr + kColR + 64 * L, oh);
     }
     if (top) {   // partial head sums; part 0 finishes the log-softmax at its next step (or after the chain)
+        float z0, z1;
+        f2_split(z01, z0, z1);
         if (part == 0) {
             c.pz = make_float4(z0, z1, y0, y1);
             c.pn = n;
