@@ -545,6 +545,7 @@ template <typename T> struct GradWs {
     double* roww;
     T *dxbuf, *Gbuf, *dzbuf;
     double* partial;
+    unsigned char* img16;   // weight image of the tensor-core base pass (FP32 probability-head models it supports)
     int ksplit, Rp, Cp;
 };
 
@@ -565,6 +566,8 @@ static GradWs<T> carve_grad(Ws& ws, const GruLayout& g, const GruLayoutT& gt, co
     const int ntile = (w.Rp / kWgTile) * (w.Cp / kWgTile);
     w.ksplit = (int)std::max<int64_t>(1, std::min<int64_t>(std::is_same<T, float>::value ? 296 : (148 * 4 + ntile - 1) / ntile, tiles * g.N));
     w.partial = ws.take<double>((size_t)w.ksplit * w.Rp * w.Cp);
+    w.img16 = nullptr;
+    if (std::is_same<T, float>::value && !cplx && tc16p::supported(g)) w.img16 = ws.take<unsigned char>(tc16p::make_layout(g).img_bytes);
     return w;
 }
 
@@ -668,7 +671,18 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.f.pk);
     prof_count(); pack_gru_T_kernel<T><<<grid_for(gt.total), 256, 0, s>>>(g, gt, (const T*)params, w.pkT);
     prof_count(); sig_transpose_kernel<<<grid_for(rows_total * g.N), 256, 0, s>>>(samples, w.f.sigT, ns, g.N, b.M, tiles_s, ndir);
-    int e = cplx ? launch_forward<T, true, true>(g, cf, w.f, tiles, s) : launch_forward<T, true, false>(g, cf, w.f, tiles, s);
+    // teacher-forced pass with stash: the tensor-core base pass where it applies (same stash layout, 128-row work items), else the
+    // FFMA tile engine
+    int e = 0;
+    bool stashed = false;
+    if constexpr (std::is_same<T, float>::value) {
+        if (w.img16 && chain_mode(g) == 3) {
+            e = tc16p::launch_eloc(g, b.M, tiles, (const float*)params, w.img16, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.la_self,
+                                   w.f.lp_re, nullptr, w.f.counter, false, s);
+            stashed = true;
+        }
+    }
+    if (!stashed) e = cplx ? launch_forward<T, true, true>(g, cf, w.f, tiles, s) : launch_forward<T, true, false>(g, cf, w.f, tiles, s);
     if (e) return e;
     prof_count(); row_weight_kernel<<<grid_for(rows_total), 256, 0, s>>>(weights, w.f.lp_re, ns, b.M, tiles_s, parity, cplx, w.roww);
     for (int l = g.L - 1; l >= 0; --l) {
