@@ -12,6 +12,7 @@
 #pragma once
 #include "gru_kernels.cuh"
 #include "host_util.cuh"
+#include "umma.cuh"
 
 namespace rnnwf {
 
@@ -458,6 +459,172 @@ __global__ void __launch_bounds__(kWgfThreads) wgrad_fast_kernel(WgradArgs<float
     }
 }
 
+// Tensor-core path of the same reduction (FP32 models): tcgen05.mma kind::tf32 with 3xTF32 operands (hi * hi + hi * lo + lo * hi,
+// FP32 accumulate in TMEM: FP32-grade products -- a single TF32 pass does not survive the cancellation in
+// sum_s (E_s - mean) d log psi_s).  Both operands are K-major with K = the samples of a (tile, site) block, which is how the stash
+// and the gate gradients already lie in HBM ([row][M], M contiguous): A = [x; h; 1] (R <= 128 rows), B = G (cols <= 256 rows), D =
+// A B^T [128 x cols] stays in TMEM across the blocks of this CTA and is flushed into its FP64 partial every kWgFlush blocks
+// (deterministic: no atomics, fixed order).  Per block: the threads split the operands they prefetched into registers during the
+// previous block's MMAs into (hi, lo) core-matrix images in shared memory, one thread issues 3 MMAs per 8 samples, and the global
+// loads of the next block are in flight while the tensor pipe works.  (The warp-level mma.sync m16n8k8 TF32 path was measured first:
+// 94 ms against the 74 ms of the FFMA kernel at cfg2 -- on sm_100a it runs at ~4x the FFMA rate, which three passes eat.)
+namespace wgtc {
+constexpr int kThreads = 256, kMaxItems = 24;
+
+struct Geo {
+    int Rp8, Cp8, Np, Kp, M4p, items, nit;      // padded A / B rows, MMA N, padded samples, float4 columns (multiple of 4)
+    size_t img_floats, smem;
+};
+inline Geo make_geo(int R, int cols, int M) {
+    Geo q;
+    q.Rp8 = (R + 7) / 8 * 8;
+    q.Cp8 = (cols + 7) / 8 * 8;
+    q.Np = (cols + 15) / 16 * 16;
+    q.Kp = (M + 7) / 8 * 8;
+    q.M4p = (M / 4 + 3) / 4 * 4;
+    q.items = (q.Rp8 + q.Cp8) * q.M4p;
+    q.nit = (q.items + kThreads - 1) / kThreads;
+    q.img_floats = (size_t)(128 + q.Np + 8) * q.Kp;                 // A image | B image (+ one row group of slack)
+    q.smem = 2 * q.img_floats * sizeof(float) + 64;
+    return q;
+}
+inline bool supported(int R, int cols, int M) {
+    if (R > 128 || cols > 256 || M % 4 != 0) return false;
+    const Geo q = make_geo(R, cols, M);
+    return q.nit <= kMaxItems && q.smem <= (size_t)kSmemLimit;
+}
+
+__device__ __forceinline__ float4 load_item(const WgradArgs<float>& a, int R, int64_t blk, int n, int row, int m4, int Rp8) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int M = a.M;
+    if (m4 >= M) return v;
+    if (row < Rp8) {
+        const int r = row;
+        if (r < a.rows0) {
+            if (a.xmode == 1) v = *reinterpret_cast<const float4*>(a.hstore + ((blk * a.L + a.lx) * a.H + r) * M + m4);
+            else if (n > 0) {
+                const uint32_t sg = *reinterpret_cast<const uint32_t*>(a.sigT + (blk - 1) * M + m4);
+                v.x = (int)(sg & 0xff) == r ? 1.f : 0.f;
+                v.y = (int)((sg >> 8) & 0xff) == r ? 1.f : 0.f;
+                v.z = (int)((sg >> 16) & 0xff) == r ? 1.f : 0.f;
+                v.w = (int)(sg >> 24) == r ? 1.f : 0.f;
+            }
+        } else if (r < a.rows0 + a.rows1) {
+            if (!(a.hshift && n == 0)) v = *reinterpret_cast<const float4*>(a.hstore + (((blk - a.hshift) * a.L + a.lh) * a.H + (r - a.rows0)) * M + m4);
+        } else if (r == R - 1) {
+            v = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+    } else {
+        const int c = row - Rp8;
+        if (c < a.cols) v = *reinterpret_cast<const float4*>(a.B + (blk * a.cols + c) * M + m4);
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, Geo q, double* __restrict__ partial, int Rp, int Cp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* img_hi = reinterpret_cast<float*>(smem);
+    float* img_lo = img_hi + q.img_floats;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(img_lo + q.img_floats);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int R = a.rows0 + a.rows1 + 1, KC = q.Kp / 4;
+    const int ks = blockIdx.x;
+    const int64_t b0 = a.nblk * ks / a.ksplit, b1 = a.nblk * (ks + 1) / a.ksplit;
+    double* out = partial + (size_t)ks * Rp * Cp;
+    for (int i = tid; i < Rp * Cp; i += blockDim.x) out[i] = 0.0;
+    for (size_t i = tid; i < 2 * q.img_floats; i += blockDim.x) img_hi[i] = 0.f;       // padding rows / samples stay zero
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 256);
+    if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_fence_init(); }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tbase = *tmem_slot;
+    const uint32_t sA_hi = umma::smem_u32(img_hi), sB_hi = sA_hi + 128u * q.Kp * 4u;
+    const uint32_t sA_lo = umma::smem_u32(img_lo), sB_lo = sA_lo + 128u * q.Kp * 4u;
+    const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, q.Np);
+    // item -> (row, float4 column): 8 consecutive lanes take the 8 rows of a core-matrix row group (one conflict-free 128-byte store),
+    // the 4 lane groups of a warp take 4 consecutive float4 columns (64 contiguous bytes of every row in global memory)
+    const int RG = (q.Rp8 + q.Cp8) / 8;
+    float4 pre[kMaxItems];
+    auto prefetch = [&](int64_t blk) {
+        const int n = (int)(blk % a.N);
+#pragma unroll
+        for (int it = 0; it < kMaxItems; ++it) {
+            const int i = tid + it * kThreads;
+            pre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (it < q.nit && i < q.items) {
+                const int b32 = i >> 5, row = (b32 % RG) * 8 + (i & 7), m4 = ((b32 / RG) * 4 + ((i >> 3) & 3)) * 4;
+                pre[it] = load_item(a, R, blk, n, row, m4, q.Rp8);
+            }
+        }
+    };
+    uint32_t commits = 0;
+    int pending = 0;
+    if (b0 < b1) prefetch(b0);
+    for (int64_t blk = b0; blk < b1; ++blk) {
+        if (commits > 0) umma::mbar_wait(bar, (commits - 1) & 1);        // the previous block's MMAs have read the images
+#pragma unroll
+        for (int it = 0; it < kMaxItems; ++it) {
+            const int i = tid + it * kThreads;
+            if (it < q.nit && i < q.items) {
+                const int b32 = i >> 5, row = (b32 % RG) * 8 + (i & 7), m4 = ((b32 / RG) * 4 + ((i >> 3) & 3)) * 4;
+                if (m4 < q.Kp) {
+                    // A rows live at image rows [0, 128), B rows at [128, 128 + Np)
+                    const int irow = row < q.Rp8 ? row : 128 + (row - q.Rp8);
+                    const size_t o = (size_t)(irow >> 3) * (KC * 32) + (size_t)(m4 >> 2) * 32 + (irow & 7) * 4;
+                    float4 hi, lo;
+                    umma::split_tf32(pre[it].x, hi.x, lo.x);
+                    umma::split_tf32(pre[it].y, hi.y, lo.y);
+                    umma::split_tf32(pre[it].z, hi.z, lo.z);
+                    umma::split_tf32(pre[it].w, hi.w, lo.w);
+                    *reinterpret_cast<float4*>(img_hi + o) = hi;
+                    *reinterpret_cast<float4*>(img_lo + o) = lo;
+                }
+            }
+        }
+        umma::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t lbo = 128, sbo = (uint32_t)KC * 128;
+            for (int kb = 0; kb < q.Kp / 8; ++kb) {
+                const uint64_t ah = umma::smem_desc(sA_hi + kb * 256, lbo, sbo), al = umma::smem_desc(sA_lo + kb * 256, lbo, sbo);
+                const uint64_t bh = umma::smem_desc(sB_hi + kb * 256, lbo, sbo), bl = umma::smem_desc(sB_lo + kb * 256, lbo, sbo);
+                umma::mma_tf32_ss(tbase, ah, bh, idesc, (pending > 0 || kb > 0) ? 1u : 0u);
+                umma::mma_tf32_ss(tbase, ah, bl, idesc, 1u);
+                umma::mma_tf32_ss(tbase, al, bh, idesc, 1u);
+            }
+            umma::commit(bar);
+        }
+        ++commits;
+        if (blk + 1 < b1) prefetch(blk + 1);                             // in flight while the tensor pipe works
+        if (++pending == kWgFlush || blk + 1 == b1) {
+            umma::mbar_wait(bar, (commits - 1) & 1);
+            umma::fence_after_sync();
+            const int row = 32 * (warp & 3) + lane, half = q.Np / 2 / 8 * 8;     // warps 0-3: columns [0, half), warps 4-7: the rest
+            const int c_lo = warp < 4 ? 0 : half, c_hi = warp < 4 ? half : q.Np;
+            for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+                float v[8];
+                umma::tmem_ld8(tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
+                umma::wait_ld();
+                if (row < R && row < Rp) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (c0 + j < a.cols && c0 + j < Cp) out[(size_t)row * Cp + c0 + j] += (double)v[j];
+                }
+            }
+            pending = 0;
+            umma::fence_before_sync();
+            __syncthreads();                                            // every warp has read its accumulators
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tbase, 256);
+}
+}  // namespace wgtc
+
 // sum the split-K partials (fixed order) and scatter into the flat gradient.
 //   layer mode : rows [x (d) | h (H) | ones], cols [da_r (H) | da_u (H) | da_c (H) | dq (H)]
 //   head mode  : rows [h_top (H) | ones],     cols [dz (2) | dz_phase (2)]
@@ -629,9 +796,19 @@ static int launch_wgrad(const GruLayout& g, const GradWs<T>& w, int M, int64_t n
     a.ksplit = w.ksplit;
     bool fast = false;
     if constexpr (std::is_same<T, float>::value) {
+        if (!head && wgtc::supported(R, a.cols, M) && !getenv("RNNWF_WGRAD_FFMA")) {
+            fast = true;
+            const wgtc::Geo q = wgtc::make_geo(R, a.cols, M);
+            auto k = wgtc::wgrad_kernel;
+            if (int e = set_smem(k, (int)q.smem)) return e;
+            prof_count(); k<<<a.ksplit, wgtc::kThreads, q.smem, s>>>(a, q, w.partial, a.rtiles * kWgTile, a.ctiles * kWgTile);
+            RNNWF_CUDA(cudaGetLastError());
+        }
+    }
+    if constexpr (std::is_same<T, float>::value) {
         const int RG = (R + kWgfTr - 1) / kWgfTr, CG = (a.cols + kWgfTc - 1) / kWgfTc;
         const size_t fsmem = (size_t)(RG * kWgfTr + CG * kWgfTc) * (M + 4) * sizeof(float);
-        if (RG * CG <= kWgfThreads && fsmem <= (size_t)kSmemLimit && RG * kWgfTr <= a.rtiles * kWgTile + 0 && !getenv("RNNWF_WGRAD_TILED")) {
+        if (!fast && RG * CG <= kWgfThreads && fsmem <= (size_t)kSmemLimit && RG * kWgfTr <= a.rtiles * kWgTile + 0 && !getenv("RNNWF_WGRAD_TILED")) {
             fast = true;
             auto k = wgrad_fast_kernel;
             if (int e = set_smem(k, (int)fsmem)) return e;
