@@ -494,32 +494,11 @@ inline bool supported(int R, int cols, int M) {
     return q.nit <= kMaxItems && q.smem <= (size_t)kSmemLimit;
 }
 
-__device__ __forceinline__ float4 load_item(const WgradArgs<float>& a, int R, int64_t blk, int n, int row, int m4, int Rp8) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int M = a.M;
-    if (m4 >= M) return v;
-    if (row < Rp8) {
-        const int r = row;
-        if (r < a.rows0) {
-            if (a.xmode == 1) v = *reinterpret_cast<const float4*>(a.hstore + ((blk * a.L + a.lx) * a.H + r) * M + m4);
-            else if (n > 0) {
-                const uint32_t sg = *reinterpret_cast<const uint32_t*>(a.sigT + (blk - 1) * M + m4);
-                v.x = (int)(sg & 0xff) == r ? 1.f : 0.f;
-                v.y = (int)((sg >> 8) & 0xff) == r ? 1.f : 0.f;
-                v.z = (int)((sg >> 16) & 0xff) == r ? 1.f : 0.f;
-                v.w = (int)(sg >> 24) == r ? 1.f : 0.f;
-            }
-        } else if (r < a.rows0 + a.rows1) {
-            if (!(a.hshift && n == 0)) v = *reinterpret_cast<const float4*>(a.hstore + (((blk - a.hshift) * a.L + a.lh) * a.H + (r - a.rows0)) * M + m4);
-        } else if (r == R - 1) {
-            v = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-    } else {
-        const int c = row - Rp8;
-        if (c < a.cols) v = *reinterpret_cast<const float4*>(a.B + (blk * a.cols + c) * M + m4);
-    }
-    return v;
-}
+// what a thread moves per block is fixed for the whole launch: item -> (source kind, element offset relative to the block's base,
+// destination in the images) is decoded once, so that the per-block code is ~8 instructions per 16-byte item (the first version
+// re-derived rows and addresses per block: 1 700 instructions per thread and block, 42 KB of unrolled code, issue-bound with
+// no_instruction stalls)
+enum { kSkip = 0, kStash = 1, kGate = 2, kOneHot = 3 };
 
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, Geo q, double* __restrict__ partial, int Rp, int Cp) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -528,12 +507,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
     uint64_t* bar = reinterpret_cast<uint64_t*>(img_lo + q.img_floats);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int R = a.rows0 + a.rows1 + 1, KC = q.Kp / 4;
+    const int R = a.rows0 + a.rows1 + 1, KC = q.Kp / 4, M = a.M;
     const int ks = blockIdx.x;
     const int64_t b0 = a.nblk * ks / a.ksplit, b1 = a.nblk * (ks + 1) / a.ksplit;
     double* out = partial + (size_t)ks * Rp * Cp;
     for (int i = tid; i < Rp * Cp; i += blockDim.x) out[i] = 0.0;
     for (size_t i = tid; i < 2 * q.img_floats; i += blockDim.x) img_hi[i] = 0.f;       // padding rows / samples stay zero
+    __syncthreads();
+    for (int i = tid; i < M; i += blockDim.x) {                                        // the constant-1 row (biases) never changes
+        const int irow = R - 1;
+        img_hi[(size_t)(irow >> 3) * (KC * 32) + (size_t)(i >> 2) * 32 + (irow & 7) * 4 + (i & 3)] = 1.0f;
+    }
     if (warp == 0) umma::tmem_alloc(tmem_slot, 256);
     if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_fence_init(); }
     umma::fence_before_sync();
@@ -546,17 +530,59 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
     // item -> (row, float4 column): 8 consecutive lanes take the 8 rows of a core-matrix row group (one conflict-free 128-byte store),
     // the 4 lane groups of a warp take 4 consecutive float4 columns (64 contiguous bytes of every row in global memory)
     const int RG = (q.Rp8 + q.Cp8) / 8;
+    int goff[kMaxItems], dsc[kMaxItems];      // element offset from the block's base; kind | zero-at-site-0 flag << 2 | one-hot row << 3 | image offset (float4) << 8
+#pragma unroll
+    for (int it = 0; it < kMaxItems; ++it) {
+        const int i = tid + it * kThreads;
+        goff[it] = 0;
+        dsc[it] = kSkip;
+        if (it < q.nit && i < q.items) {
+            const int b32 = i >> 5, row = (b32 % RG) * 8 + (i & 7), m4 = ((b32 / RG) * 4 + ((i >> 3) & 3)) * 4;
+            if (m4 < M) {
+                const int irow = row < q.Rp8 ? row : 128 + (row - q.Rp8);
+                const int o4 = (int)(((size_t)(irow >> 3) * (KC * 32) + (size_t)(m4 >> 2) * 32 + (irow & 7) * 4) >> 2);
+                int kind = kSkip, flags = 0, off = 0;
+                if (row < q.Rp8) {
+                    const int r = row;
+                    if (r < a.rows0) {
+                        if (a.xmode == 1) { kind = kStash; off = (a.lx * a.H + r) * M + m4; }
+                        else { kind = kOneHot; flags = r << 3; off = m4 - M; }                 // sigT of block blk - 1
+                    } else if (r < a.rows0 + a.rows1) {
+                        kind = kStash;
+                        off = ((a.lh - a.hshift * a.L) * a.H + (r - a.rows0)) * M + m4;        // hstore of block blk - hshift
+                        flags = a.hshift ? 4 : 0;
+                    }
+                } else if (row - q.Rp8 < a.cols) {
+                    kind = kGate;
+                    off = (row - q.Rp8) * M + m4;
+                }
+                goff[it] = off;
+                dsc[it] = kind | flags | (o4 << 8);
+            }
+        }
+    }
+    const int64_t hspan = (int64_t)a.L * a.H * M, gspan = (int64_t)a.cols * M;
     float4 pre[kMaxItems];
     auto prefetch = [&](int64_t blk) {
-        const int n = (int)(blk % a.N);
+        const bool first_site = blk % a.N == 0;
+        const float* hb = a.hstore + blk * hspan;
+        const float* gb = a.B + blk * gspan;
+        const uint8_t* sb = a.sigT + blk * M;
 #pragma unroll
         for (int it = 0; it < kMaxItems; ++it) {
-            const int i = tid + it * kThreads;
-            pre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (it < q.nit && i < q.items) {
-                const int b32 = i >> 5, row = (b32 % RG) * 8 + (i & 7), m4 = ((b32 / RG) * 4 + ((i >> 3) & 3)) * 4;
-                pre[it] = load_item(a, R, blk, n, row, m4, q.Rp8);
+            const int kind = dsc[it] & 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kind == kGate) v = *reinterpret_cast<const float4*>(gb + goff[it]);
+            else if (kind == kStash) { if (!((dsc[it] & 4) && first_site)) v = *reinterpret_cast<const float4*>(hb + goff[it]); }
+            else if (kind == kOneHot && !first_site) {
+                const uint32_t sg = *reinterpret_cast<const uint32_t*>(sb + goff[it]);
+                const int r = (dsc[it] >> 3) & 31;
+                v.x = (int)(sg & 0xff) == r ? 1.f : 0.f;
+                v.y = (int)((sg >> 8) & 0xff) == r ? 1.f : 0.f;
+                v.z = (int)((sg >> 16) & 0xff) == r ? 1.f : 0.f;
+                v.w = (int)(sg >> 24) == r ? 1.f : 0.f;
             }
+            pre[it] = v;
         }
     };
     uint32_t commits = 0;
@@ -566,21 +592,15 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
         if (commits > 0) umma::mbar_wait(bar, (commits - 1) & 1);        // the previous block's MMAs have read the images
 #pragma unroll
         for (int it = 0; it < kMaxItems; ++it) {
-            const int i = tid + it * kThreads;
-            if (it < q.nit && i < q.items) {
-                const int b32 = i >> 5, row = (b32 % RG) * 8 + (i & 7), m4 = ((b32 / RG) * 4 + ((i >> 3) & 3)) * 4;
-                if (m4 < q.Kp) {
-                    // A rows live at image rows [0, 128), B rows at [128, 128 + Np)
-                    const int irow = row < q.Rp8 ? row : 128 + (row - q.Rp8);
-                    const size_t o = (size_t)(irow >> 3) * (KC * 32) + (size_t)(m4 >> 2) * 32 + (irow & 7) * 4;
-                    float4 hi, lo;
-                    umma::split_tf32(pre[it].x, hi.x, lo.x);
-                    umma::split_tf32(pre[it].y, hi.y, lo.y);
-                    umma::split_tf32(pre[it].z, hi.z, lo.z);
-                    umma::split_tf32(pre[it].w, hi.w, lo.w);
-                    *reinterpret_cast<float4*>(img_hi + o) = hi;
-                    *reinterpret_cast<float4*>(img_lo + o) = lo;
-                }
+            if ((dsc[it] & 3) != kSkip) {
+                const size_t o = (size_t)(dsc[it] >> 8) << 2;
+                float4 hi, lo;
+                umma::split_tf32(pre[it].x, hi.x, lo.x);
+                umma::split_tf32(pre[it].y, hi.y, lo.y);
+                umma::split_tf32(pre[it].z, hi.z, lo.z);
+                umma::split_tf32(pre[it].w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(img_hi + o) = hi;
+                *reinterpret_cast<float4*>(img_lo + o) = lo;
             }
         }
         umma::fence_proxy_async();
