@@ -595,10 +595,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
             if ((dsc[it] & 3) != kSkip) {
                 const size_t o = (size_t)(dsc[it] >> 8) << 2;
                 float4 hi, lo;
-                umma::split_tf32(pre[it].x, hi.x, lo.x);
-                umma::split_tf32(pre[it].y, hi.y, lo.y);
-                umma::split_tf32(pre[it].z, hi.z, lo.z);
-                umma::split_tf32(pre[it].w, hi.w, lo.w);
+                umma::split_tf32_fast(pre[it].x, hi.x, lo.x);      // integer rounding: cvt.rna.tf32 issues at a quarter of the ALU rate
+                umma::split_tf32_fast(pre[it].y, hi.y, lo.y);
+                umma::split_tf32_fast(pre[it].z, hi.z, lo.z);
+                umma::split_tf32_fast(pre[it].w, hi.w, lo.w);
                 *reinterpret_cast<float4*>(img_hi + o) = hi;
                 *reinterpret_cast<float4*>(img_lo + o) = lo;
             }
