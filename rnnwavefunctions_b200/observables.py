@@ -31,8 +31,7 @@ def _u8(wf, samples):
 
 def sz_moments(samples, device=None):
     """samples [ns, N] (0/1, host or device) -> (<sz_i> [N], <sz_i sz_j> [N, N]) as float64 device tensors.
-    The second moment is one exact library GEMM of +-1 values (sums below 2^24 are exact in FP32 accumulation of the
-    float64 GEMM used here)."""
+    The second moment is one plain library GEMM of +-1 values in float64 (integer-valued sums: exact)."""
     s = torch.as_tensor(samples)
     if device is not None:
         s = s.to(device)

@@ -76,3 +76,27 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_lr_schedules_match_the_reference_formulas():
+    """constant (1DTFIM/TrainingRNN_1DTFIM.py:221), 1/((1/lr)+it/10) (2DTFIM_1DRNN/Training1DRNN_2DTFIM.py:229),
+    lr (1+it/5000)^-1 (2DTFIM_2DRNN/Training2DRNN_2DTFIM.py:228)."""
+    import inspect
+
+    import pytest
+
+    from rnnwavefunctions_b200 import training as TR
+    lr = 5e-3
+    assert TR._schedule(lr, None)(1234) == lr and TR._schedule(lr, "constant")(0) == lr
+    inv = TR._schedule(lr, "inverse")
+    assert inv(0) == pytest.approx(lr) and inv(70) == pytest.approx(1.0 / (1.0 / lr + 7.0))
+    inv5 = TR._schedule(lr, "inverse5000")
+    assert inv5(0) == pytest.approx(lr) and inv5(5000) == pytest.approx(lr / 2)
+    assert TR._schedule(lr, lambda it: 7.0)(3) == 7.0
+    with pytest.raises(ValueError):
+        TR._schedule(lr, "cosine")
+    # the drivers keep the schedules the reference ships as their defaults
+    assert inspect.signature(TR.run_1DTFIM).parameters["lr_schedule"].default is None
+    assert inspect.signature(TR.run_2DTFIM_1DRNN).parameters["lr_schedule"].default == "inverse"
+    assert inspect.signature(TR.run_2DTFIM_2DRNN).parameters["lr_schedule"].default == "inverse5000"
+    assert inspect.signature(TR.run_J1J2).parameters["lr_schedule"].default is None
