@@ -81,3 +81,26 @@ def test_tc_j1j2_exchange_chains_match_ffma_and_oracle(L, N, ns, marshall, j2):
         assert np.abs(out[chain][0] - ref).max() < 3e-5 * scale              # the reference combine is complex64
         np.testing.assert_allclose(out[chain][1].real, la_ref.real, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(out[chain][1].imag, la_ref.imag, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("ns", [1, 3, 129, 257])
+def test_ragged_sample_counts_local_energies_and_gradient(ns):
+    """Sample counts that do not fill a tile (1, 3) or spill one row into the next 128-row work item (129, 257): local energies on
+    the pipelined tensor-core kernel (3-layer specialised copies) against the full-recompute oracle, and the VMC gradient (stash
+    pass on the tensor-core base kernel, weight-gradient reduction on tcgen05 3xTF32) against CPU autograd."""
+    from oracle import torch_grad as TG
+    L, N = 3, 12
+    p = O.randomize_biases(O.init_gru_params([50] * L, seed=7, dtype=np.float32, scale=2.0), seed=8)
+    model = ops.make_model(num_layers=L, units=50, n_sites=N)
+    flat = torch.tensor(O.flatten(p), device=dev())
+    s = O.sample(p, ns, N, seed=11)
+    Jz = np.random.default_rng(2).uniform(0.5, 1.5, size=N)
+    e, lp = ops.tfim_eloc(model, flat, u8(s), Jz, 1.1)
+    ref = O.ising_local_energies(Jz, 1.1, s, lambda c: O.log_probability(p, c))
+    np.testing.assert_allclose(e.cpu().numpy(), ref, rtol=1e-5)
+    np.testing.assert_allclose(lp.cpu().numpy(), O.log_probability(p, s), rtol=1e-5)
+    w = np.random.default_rng(ns).normal(size=ns) / ns
+    got = ops.vmc_grad(model, flat, u8(s), torch.tensor(w, device=dev())).cpu().numpy()
+    want = TG.gru_vmc_grad({k: v.astype(np.float64) for k, v in p.items()}, s, w)
+    err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    assert err < 1e-4, err
