@@ -131,8 +131,8 @@ gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __
     off += (size_t)H * M * sizeof(T);
     T* G = reinterpret_cast<T*>(smem + off);
     off += (size_t)4 * H * M * sizeof(T);
-    T* dz = reinterpret_cast<T*>(smem + off);
-    off += (size_t)4 * M * sizeof(T);
+    T* dz = reinterpret_cast<T*>(smem + off);       // two buffers of 4 * M
+    off += (size_t)8 * M * sizeof(T);
     uint8_t* codes = smem + off;
 
     const bool is_compute = tid < CT * c.RT;
@@ -158,43 +158,67 @@ gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __
         for (int s = 0; s < SPT; ++s) carry[u][s] = T(0);
     __syncthreads();
 
-    for (int n = N - 1; n >= 0; --n) {
+    // (a) staging of a site's inputs, one site ahead of the arithmetic: h_prev = h^l_{n-1}, x = h^{l-1}_n (or the one-hot code of
+    // sigma_{n-1}) arrive by cp.async while phase (e) of the site before runs (xs / hp / codes are only read in phase (c)); the head
+    // gradients dz of the top layer are double-buffered.  (ncu on the synchronous version: long_scoreboard 1.85 stalls per issue.)
+    auto stage_inputs = [&](int n) {
         const size_t blk = (size_t)st * N + n;
-        {   // (a) stage the inputs of site n:  h_prev = h^l_{n-1},  x = h^{l-1}_n  (or the one-hot code of sigma_{n-1})
-            const T* hsrc = n > 0 ? hstore + ((blk - 1) * L + l) * H * M : nullptr;
-            for (int i = tid; i < H * M; i += blockDim.x) hp[i] = hsrc ? hsrc[i] : T(0);
-            if (l > 0) {
-                const T* xsrc = hstore + (blk * L + (l - 1)) * H * M;
-                for (int i = tid; i < d * M; i += blockDim.x) xs[i] = xsrc[i];
+        const uint32_t hp_s = (uint32_t)__cvta_generic_to_shared(hp), xs_s = (uint32_t)__cvta_generic_to_shared(xs);
+        const uint32_t cd_s = (uint32_t)__cvta_generic_to_shared(codes);
+        if (n > 0) {
+            const char* hsrc = reinterpret_cast<const char*>(hstore + ((blk - 1) * L + l) * H * M);
+            for (int i = tid; i < (int)(H * M * sizeof(T) / 16); i += blockDim.x)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hp_s + 16 * i), "l"(hsrc + 16 * (size_t)i) : "memory");
+        } else {
+            for (int i = tid; i < H * M; i += blockDim.x) hp[i] = T(0);
+        }
+        if (l > 0) {
+            const char* xsrc = reinterpret_cast<const char*>(hstore + (blk * L + (l - 1)) * H * M);
+            for (int i = tid; i < (int)(d * M * sizeof(T) / 16); i += blockDim.x)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_s + 16 * i), "l"(xsrc + 16 * (size_t)i) : "memory");
+        } else if (n > 0) {
+            const uint8_t* csrc = sigT + (blk - 1) * M;
+            for (int i = tid; i < M / 4; i += blockDim.x)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cd_s + 4 * i), "l"(csrc + 4 * (size_t)i) : "memory");
+        } else {
+            for (int m = tid; m < M; m += blockDim.x) codes[m] = (uint8_t)2;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto stage_dz = [&](int n, T* dzd) {
+        const size_t blk = (size_t)st * N + n;
+        for (int m = tid; m < M; m += blockDim.x) {
+            const int sg = sigT[blk * M + m];
+            const double lo = la_oth[blk * M + m];
+            const double wre = roww[(size_t)st * M + m];
+            T z[4] = {0, 0, 0, 0};
+            if (!CPLX) {
+                const double t = wre * exp(lo);        // w (1 - p_sel) = w p_oth
+                z[sg] = (T)t;
+                z[1 - sg] = (T)(-t);
             } else {
-                for (int m = tid; m < M; m += blockDim.x) codes[m] = n > 0 ? sigT[(blk - 1) * M + m] : (uint8_t)2;
+                const double t = 0.5 * wre * exp(2.0 * lo);   // d(1/2 log p_sel)/dz ; 0 when the other outcome is masked
+                z[sg] = (T)t;
+                z[1 - sg] = (T)(-t);
+                const double y = fabs(ph_sel[blk * M + m]) / kPi;
+                z[2 + sg] = (T)(roww[rows_total + (size_t)st * M + m] * kPi * (1.0 - y) * (1.0 - y));
             }
-            if (top) {
-                for (int m = tid; m < M; m += blockDim.x) {
-                    const int sg = sigT[blk * M + m];
-                    const double lo = la_oth[blk * M + m];
-                    const double wre = roww[(size_t)st * M + m];
-                    T z[4] = {0, 0, 0, 0};
-                    if (!CPLX) {
-                        const double t = wre * exp(lo);        // w (1 - p_sel) = w p_oth
-                        z[sg] = (T)t;
-                        z[1 - sg] = (T)(-t);
-                    } else {
-                        const double t = 0.5 * wre * exp(2.0 * lo);   // d(1/2 log p_sel)/dz ; 0 when the other outcome is masked
-                        z[sg] = (T)t;
-                        z[1 - sg] = (T)(-t);
-                        const double y = fabs(ph_sel[blk * M + m]) / kPi;
-                        z[2 + sg] = (T)(roww[rows_total + (size_t)st * M + m] * kPi * (1.0 - y) * (1.0 - y));
-                    }
 #pragma unroll
-                    for (int o = 0; o < NZ; ++o) {
-                        dz[o * M + m] = z[o];
-                        dzbuf[(blk * NZ + o) * M + m] = z[o];
-                    }
-                }
+            for (int o = 0; o < NZ; ++o) {
+                dzd[o * M + m] = z[o];
+                dzbuf[(blk * NZ + o) * M + m] = z[o];
             }
         }
-        __syncthreads();
+    };
+    T* dz_cur = dz;
+    T* dz_nxt = dz + 4 * M;
+    stage_inputs(N - 1);
+    if (top) stage_dz(N - 1, dz_cur);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    for (int n = N - 1; n >= 0; --n) {
+        const size_t blk = (size_t)st * N + n;
         T cdir[2][SPT];
         if (is_compute) {   // (c) recompute gates, local backward, publish gate gradients
             T ar[2][SPT], au[2][SPT], ac[2][SPT], aq[2][SPT];
@@ -208,8 +232,8 @@ gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __
                     if (top) {
 #pragma unroll
                         for (int s = 0; s < SPT; ++s) {
-                            T v = dz[row0 + s] * wd[u][0] + dz[M + row0 + s] * wd[u][1];
-                            if (CPLX) v += dz[2 * M + row0 + s] * wd[u][2] + dz[3 * M + row0 + s] * wd[u][3];
+                            T v = dz_cur[row0 + s] * wd[u][0] + dz_cur[M + row0 + s] * wd[u][1];
+                            if (CPLX) v += dz_cur[2 * M + row0 + s] * wd[u][2] + dz_cur[3 * M + row0 + s] * wd[u][3];
                             dout[s] = v;
                         }
                     } else {
@@ -244,6 +268,10 @@ gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __
             }
         }
         __syncthreads();
+        if (n > 0) {        // inputs of site n - 1: in flight while (e) runs
+            stage_inputs(n - 1);
+            if (top) stage_dz(n - 1, dz_nxt);
+        }
         if (is_compute) {   // (e) d h_{n-1} and d x through the transposed weights
             T accH[2][SPT], accX[2][SPT];
 #pragma unroll
@@ -288,8 +316,11 @@ gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __
                 }
             }
         }
-        // next iteration's (a) only writes xs/hp/dz/codes, which nobody reads in (e); the barrier after (a)
-        // orders (e) before the next (c) rewrites G.
+        // the staging above only writes xs / hp / codes / the other dz buffer, which nobody reads in (e); this barrier makes them
+        // visible and orders (e) before the next (c) rewrites G.
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        { T* tmp = dz_cur; dz_cur = dz_nxt; dz_nxt = tmp; }
     }
 }
 
@@ -700,7 +731,7 @@ template <typename T> inline BwdLaunch choose_bwd_launch(const GruLayout& g, int
             if (nt > 384 || M > 2 * kHeadThreads) break;
             const int Mp = (M + 15) & ~15;
             size_t smem = (wsm ? (((size_t)(maxpk + 2 * per) * sizeof(T) + 15) & ~(size_t)15) : 0) +
-                          (size_t)(dmax + g.H + 4 * g.H + 4) * M * sizeof(T) + Mp + 64;
+                          (size_t)(dmax + g.H + 4 * g.H + 8) * M * sizeof(T) + Mp + 64;
             // the forward pass of the gradient runs with the same M: all layers' weights + L*H*M state
             size_t fwd = (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) + (size_t)g.L * g.H * M * sizeof(T) + 2 * (size_t)Mp + 64;
             if (smem > (size_t)kSmemLimit) break;
