@@ -222,6 +222,14 @@ gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __
         T cdir[2][SPT];
         if (is_compute) {   // (c) recompute gates, local backward, publish gate gradients
             T ar[2][SPT], au[2][SPT], ac[2][SPT], aq[2][SPT];
+            T dpre[2][SPT];                     // d h^l_n from the layer above: loaded ahead of the gate GEMM that hides its latency
+            if (!top) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = 2 * ct + u;
+                    if (j < H) ldv<SPT>(dpre[u], dxbuf + (blk * H + j) * M + row0);
+                }
+            }
             gru_preact<T>(g, l, wl, l == 0 ? nullptr : xs, hp, codes, M, ct, rt, ar, au, ac, aq);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -237,7 +245,8 @@ gru_bwd_layer_kernel(GruLayout g, GruLayoutT gt, BwdLaunch c, int l, const T* __
                             dout[s] = v;
                         }
                     } else {
-                        ldv<SPT>(dout, dxbuf + (blk * H + j) * M + row0);
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) dout[s] = dpre[u][s];
                     }
 #pragma unroll
                     for (int s = 0; s < SPT; ++s) {
