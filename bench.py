@@ -277,10 +277,10 @@ def run_b200_arm(args):
         # 2*128*N*K flops each
         tiles128 = -(-(ndir * (-(-ns // 120)) * 120) // 128)
         if mode == 3:
-            per_l0 = 2 * 128 * 16 * (2 + 12) * 176        # x group: 2 one-hot MMAs, h group: 12 (the first split 112 + 64), N = 176
-            per_l1 = 2 * 128 * 16 * 24 * 176
+            per_l0 = 2 * 128 * 16 * ((2 + 11) * 160 + 176)   # x group: 2 one-hot MMAs, h group: 12 (the first split 112 + 64), N = 160
+            per_l1 = 2 * 128 * 16 * (23 * 160 + 176)
             kname = ("tc16p::chain_kernel<false,false> (tcgen05 kind::f16, 3xFP16 operands, weights resident in shared memory, merged "
-                     "N=176 gate-block MMAs, MMA and gate math software-pipelined over anti-diagonals of the (site, layer) grid, one "
+                     "N=160 gate-block MMAs, MMA and gate math software-pipelined over anti-diagonals of the (site, layer) grid, one "
                      "specialised step copy per layer)")
         elif mode == 2:
             per_l0 = 2 * 128 * 16 * (2 * 160 + 64 + 12 * 160)
@@ -303,8 +303,8 @@ def run_b200_arm(args):
                         note_rooflines="peak_over_passes = tensor peak / 3: the ceiling of any 3-pass split-operand scheme with FP32-grade accuracy on "
                                        "this pipe; tf32x3_roofline = (16-bit peak / 2) / 3: the ceiling of the 3xTF32 scheme BASELINE.json's north_star names",
                         note="achieved counts ALGORITHMIC flops (75 800 per GRU-stack evaluation); FP32-grade accuracy costs 3 tensor passes "
-                             "over padded tiles (K 51 -> 64, N 150 -> 176), so the tensor pipe executes ~3.6-4x the algorithmic flops; the "
-                             "instructions are N = 176 wide because one with a new A chunk pays ~81 cycles of TMEM operand fetch whatever its N "
+                             "over padded tiles (K 51 -> 64, N 150 -> 160), so the tensor pipe executes ~3.6-4x the algorithmic flops; the "
+                             "instructions are N = 160 wide because one with a new A chunk pays ~81 cycles of TMEM operand fetch whatever its N "
                              "(measured, scripts/mma_probe2.py); the recurrence leaves one (site, layer) step of look-ahead and a single "
                              "accumulator set fits TMEM, so the gate math (XU pipe ~70 % busy, ncu) and the MMAs (tensor pipe ~71 %) overlap "
                              "step against step")

@@ -18,21 +18,24 @@
 //   * all row-warp <-> MMA-warp hand-offs are mbarriers (no CTA-wide bar.sync in the site loop).
 //   * ONE copy of the step code serves both unit halves of a row and every layer (measured: with the fully specialised
 //     150 KB loop body of the first version the SMs of a GPC ran at the speed of their shared instruction fetch path — the
-//     first TPC of each GPC at 4 500 cycles per step, the others at 6 500 - 10 000).  The two row threads of a sample own 25
-//     units each, placed at aligned TMEM columns so that the same instructions work for either half with a runtime offset;
-//     the per-layer hidden-state registers are rotated with moves instead of unrolling the layer loop.
-// Generation 3b: the x operand feeds ONE instruction group [cx | r | u] (N = 176) and the h operand ONE group [r | u | ch]
-// (N = 176): a tcgen05.mma with a new A chunk costs ~81 cycles of TMEM operand fetch whatever its N (scripts/mma_probe2.py), so
-// 24 wide instructions (~2 150 cycles per step, tensor-throughput bound) replace 48 narrow ones (~3 300, operand-fetch bound).
+//     first TPC of each GPC at 4 500 cycles per step, the others at 6 500 - 10 000).  The two row threads of a sample own 26
+//     units each (0..25 and 24..49: two units are computed twice), which puts both halves at 4-aligned TMEM columns (tcgen05.ld/st
+//     fault on others) with gate blocks only 52 wide; the same instructions work for either half with a runtime offset.
+//     (3c: three-layer stacks run one statically specialised copy of the step per layer instead -- see row_chain.)
+// Generation 3b: the x operand feeds ONE instruction group [cx | r | u] (N = 160) and the h operand ONE group [r | u | ch]
+// (N = 160): a tcgen05.mma with a new A chunk costs ~81 cycles of TMEM operand fetch whatever its N (scripts/mma_probe2.py), so
+// 24 wide instructions (tensor-throughput bound) replace 48 narrow ones (~3 300 cycles per step, operand-fetch bound).
 // One commit per step; the row warps pull the whole accumulator set into registers first, release it (acc_free) and do all the
 // gate math while the tensor pipe already runs the next step.
-// TMEM columns: junk [0,8) | D_cx [8,64) | D_r [64,120) D_u [120,176) | D_ch [176,232) | junk [232,240) |
-//               R_l (h^l: 32 hi + 32 lo packed half pairs) at 240 + 64 l | X0 (one-hot input of layer 0) at 240 + 64 L.
-//   gate block (56 columns): unit j < 25 at column j, unit j >= 25 at column j + 3 (second half starts at 28)
-//   operand region (K = 64):  unit j < 25 at k = j, the constant 1 (bias column) at k = 25, unit j >= 25 at k = j + 7 (32..56)
-// Shared memory: per layer the K-major core-matrix images H_hi | H_lo | X_hi | X_lo, 168 rows each: H = [r(56) | u(56) | ch(56)],
-// X = [cx(56) | r(56) | u(56)].  The N = 176 instructions of the h operand run 8 rows (one row group) into whatever follows the
-// image, those of the x operand START one row group before it: the stray rows only feed the junk accumulator columns.
+// TMEM columns: D_cx [0,52) | D_r [52,104) D_u [104,156) | D_ch [156,208) | junk [208,220) |
+//               R_l (h^l: 32 hi + 32 lo packed half pairs) at 224 + 64 l | X0 (one-hot input of layer 0) at 224 + 64 L.
+//   gate block (52 columns): unit j at column j, columns 50, 51 unused
+//   operand region (K = 64):  unit j at k = j, the constant 1 (bias column) at k = 50 (set once per CTA)
+// Shared memory: per layer the K-major core-matrix images H_hi | H_lo | X_hi | X_lo, 160 rows each: H = [r(52) | u(52) | ch(52) | 4
+// zero rows], X = [cx(52) | r(52) | u(52) | 4 zero rows].  The x group writes D columns [0, 160) (its zero rows add nothing to the
+// first ch columns), the h group [52, 212); the instruction that opens the h group is split in two because it accumulates onto
+// r, u but must overwrite ch: [r | u] N = 112 (8 stray columns into ch) and then ch N = 64 from B row 104 (a row-group boundary; it
+// runs 8 rows into whatever follows the image: junk columns).
 // Included by gru.cu.
 #pragma once
 #include "gru_tc16.cuh"
@@ -79,17 +82,19 @@ __device__ __forceinline__ f2_t neg_rcp2(float a, float b) {
 __device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 constexpr int kRows = 128, kRowThreads = 256, kThreads = 384, kMmaWarp = 8;   // warps 9-11 only complete the MMA warp's warpgroup (setmaxnreg)
-constexpr int kUP = 25;                                  // units per row thread (H = 50, two threads per row)
-constexpr int kBW = 56;                                  // accumulator columns per gate block
-constexpr int kNAll = 176, kNRU = 112, kNC = 64;         // N of the merged instructions; of the two that open the h group
-constexpr int kRowsImg = 168;                            // stored B rows of an image: three gate blocks
+constexpr int kUP = 26, kPU = 24;                        // units per row thread; first unit of part 1: part p owns units [24 p, 24 p + 26),
+                                                         // units 24 and 25 are computed (identically) by both threads of a sample, so that
+                                                         // both halves start at a 4-aligned column and the gate blocks are 52 wide, not 56
+constexpr int kBW = 52;                                  // accumulator columns per gate block: unit j at column j, 2 junk columns
+constexpr int kNAll = 160, kNRU = 112, kNC = 64;         // N of the merged instructions; of the two that open the h group
+constexpr int kRowsImg = 160;                            // stored B rows of an image: three gate blocks + 4 zero rows
 constexpr int kKp = 64, kKC = 8;                         // K padded to 4 MMA steps of 16; 16-byte chunks per row
-constexpr int kColX = 0, kColCX = 8, kColRU = 64, kColCH = 176, kColR = 240;   // kColX: D base of the x group (junk | cx | r | u)
-constexpr int kKOne = kUP;                               // K index of the constant-1 (bias) column
+constexpr int kColX = 0, kColCX = 0, kColRU = 52, kColCH = 156, kColR = 224;   // kColX: D base of the x group (cx | r | u)
+constexpr int kKOne = 50;                                // K index of the constant-1 (bias) column
 enum { kFull = 0, kAccFree = 1, kCDone = 2, kWImg = 3, kNumBars = 4 };
 
-__host__ __device__ __forceinline__ int unit_of_col(int c) { return c < kUP ? c : (c >= 28 && c < 28 + kUP ? c - 3 : -1); }   // gate-block column -> unit
-__host__ __device__ __forceinline__ int unit_of_k(int k) { return k < kUP ? k : (k >= 32 && k < 32 + kUP ? k - 7 : -1); }     // operand K index -> unit
+__host__ __device__ __forceinline__ int unit_of_col(int c) { return c < 50 ? c : -1; }   // gate-block column -> unit
+__host__ __device__ __forceinline__ int unit_of_k(int k) { return k < 50 ? k : -1; }     // operand K index -> unit
 
 struct Layout {
     int L, H, N;
@@ -148,7 +153,7 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         const int blk = n / kBW;
         const bool cand = xpart ? blk == 0 : blk == 2;
         const int gate = xpart ? blk - 1 : blk;                  // 0: r, 1: u (unused for the candidate block)
-        const int j = unit_of_col(n % kBW);                      // output unit of this row (-1: padding)
+        const int j = blk < 3 ? unit_of_col(n % kBW) : -1;       // output unit of this row (-1: padding)
         const int ku = unit_of_k(k);                             // input unit of this K index (-1: constant / padding)
         float v = 0.f;
         int KC = kKC;
@@ -183,11 +188,14 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         reinterpret_cast<__half*>(lo_b)[core_off(n, k, KC)] = __float2half_rn(v - __half2float(hi));
     }
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < t.tab_floats; idx += gridDim.x * blockDim.x) {
-        const int hd = idx / 132, r = idx % 132;        // per head: Wd[j][2] (64 x 2) | bd[2] | pad
+        const int hd = idx / 132, r = idx % 132;        // per head: [part][slot (26)][2] weights of unit 24 part + slot | pad | bd[2] at 128 | pad
         const float* hw = flat + g.flat_head + hd * (2 * H + 2);
         float v = 0.f;
-        if (r < 128) { if (r / 2 < H) v = hw[r]; }
-        else if (r < 130) v = hw[2 * H + (r - 128)];
+        if (r < 4 * kUP) {                              // part 1's first two slots duplicate units 24, 25 of part 0: zero weights
+            const int part = r / (2 * kUP), slot = (r % (2 * kUP)) / 2, o = r & 1;
+            if (!(part == 1 && slot < kUP - kPU)) v = hw[2 * (kPU * part + slot) + o];
+        }
+        else if (r >= 128 && r < 130) v = hw[2 * H + (r - 128)];
         reinterpret_cast<float*>(img + t.tab_off)[idx] = v;
     }
 }
@@ -217,12 +225,11 @@ template <int NC> __device__ __forceinline__ void stage_cols(uint32_t col, const
         umma::tmem_st1(col + 32, lo);
     }
 }
-// the 25 units of a row thread (+ its half of the constant-1 column) -> columns [16 part, 16 part + 13) of an operand region
-__device__ __forceinline__ void stage_all(uint32_t reg_part_addr, const float* hp, float one) {
+// the 26 units of a row thread -> columns [12 part, 12 part + 13) of an operand region
+__device__ __forceinline__ void stage_all(uint32_t reg_part_addr, const float* hp) {
 #pragma unroll
     for (int gq = 0; gq < 3; ++gq) stage_cols<4>(reg_part_addr + 4 * gq, hp + 8 * gq);
-    const float tail[2] = {hp[24], one};
-    stage_cols<1>(reg_part_addr + 12, tail);
+    stage_cols<1>(reg_part_addr + 12, hp + 24);
 }
 
 struct Args {
@@ -404,7 +411,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     const int N = a.g.N, Mold = a.Mold, part = c.part;
     const bool top = l == L - 1;
     const uint32_t par = c.g & 1;
-    const uint32_t dpart = c.lane_addr + 28 * part;                       // this thread's columns inside a gate block
+    const uint32_t dpart = c.lane_addr + kPU * part;                      // this thread's columns inside a gate block
     // global loads this step will need at its end are issued before the wait (part 0): the spin of site n (one-hot input of
     // (n + 1, 0) / selected outcome of the head) and the base-pass terms of site n
     int spin_n = 0;
@@ -433,15 +440,15 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
         umma::tmem_ld8p(dpart + kColRU + 8 * gq, rr + 8 * gq);
         umma::tmem_ld8p(dpart + kColRU + kBW + 8 * gq, uu + 8 * gq);
     }
-    umma::tmem_ld1p(dpart + kColRU + 24, rr + 24);
-    umma::tmem_ld1p(dpart + kColRU + kBW + 24, uu + 24);
+    umma::tmem_ld2p(dpart + kColRU + 24, rr + 24);
+    umma::tmem_ld2p(dpart + kColRU + kBW + 24, uu + 24);
 #pragma unroll
     for (int gq = 0; gq < 3; ++gq) {
         umma::tmem_ld8p(dpart + kColCX + 8 * gq, dc + 8 * gq);
         umma::tmem_ld8p(dpart + kColCH + 8 * gq, dq + 8 * gq);
     }
-    umma::tmem_ld1p(dpart + kColCX + 24, dc + 24);
-    umma::tmem_ld1p(dpart + kColCH + 24, dq + 24);
+    umma::tmem_ld2p(dpart + kColCX + 24, dc + 24);
+    umma::tmem_ld2p(dpart + kColCH + 24, dq + 24);
     umma::wait_ld();
     umma::fence_before_sync();
     umma::mbar_arrive(&c.bars[kAccFree]);              // the accumulators may be overwritten by the next step's MMAs
@@ -456,20 +463,19 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     // ex2 / rcp is bound by the 4-lane XU pipe while the issue slots idle
 #if !RNNWF_FUSED
 #pragma unroll
-    for (int q = 0; q < kUP - 1; q += 2) ru_pair(rr[q], uu[q], rr[q + 1], uu[q + 1]);
-    ru_one(rr[kUP - 1], uu[kUP - 1]);
+    for (int q = 0; q < kUP; q += 2) ru_pair(rr[q], uu[q], rr[q + 1], uu[q + 1]);
 #endif
     TCP_T(long long t3 = clock64(); c.t_ru += t3 - t2;)
     // ---- candidate, new state, head partial sums, restaging
-    const uint32_t reg = c.lane_addr + kColR + 64 * l + 16 * part;
+    const uint32_t reg = c.lane_addr + kColR + 64 * l + (kPU / 2) * part;
     const float* tab = c.tab + 2 * kUP * part;
-    float* hst = BASE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kUP * part) * Mold + c.m : nullptr;
+    float* hst = BASE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kPU * part) * Mold + c.m : nullptr;
     float y0 = 0.f, y1 = 0.f;
     f2_t z01 = f2_make(0.f, 0.f);                      // head partial sums (z0, z1), one packed FMA per unit
 #pragma unroll
-    for (int gq = 0; gq < 3; ++gq) {
+    for (int gq = 0; gq < 4; ++gq) {                   // three column groups of 4 unit pairs and the 13th pair
 #pragma unroll
-        for (int q = 0; q < 8; q += 2) {
+        for (int q = 0; q < (gq < 3 ? 8 : 2); q += 2) {
             const int jl = 8 * gq + q;
 #if RNNWF_FUSED
             ru_pair(rr[jl], uu[jl], rr[jl + 1], uu[jl + 1]);
@@ -521,28 +527,8 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
             }
         }
         // region l takes the new state: it is the h operand of (n + 1, l) and the x operand of (n, l + 1), both visited later
-        stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
-    }
-    {   // unit 24 of this half, staged next to this half's share of the constant-1 column
-        const int jl = kUP - 1;
-#if RNNWF_FUSED
-        ru_one(rr[jl], uu[jl]);
-#endif
-        const float ec = 1.0f + ex2(fminf(fmaf(rr[jl], dq[jl], dc[jl]), 60.f));
-        const float cc = fmaf(-2.0f, rcp(ec), 1.0f);
-        const float h0 = fmaf(uu[jl], hp[jl] - cc, cc);
-        hp[jl] = h0;
-        if (top) {
-            const float2 w0 = *reinterpret_cast<const float2*>(tab + 2 * jl);
-            z01 = f2_fma(f2_make(h0, h0), f2_make(w0.x, w0.y), z01);
-            if (CPLX) {
-                y0 = fmaf(h0, tab[132 + 2 * jl], y0);
-                y1 = fmaf(h0, tab[132 + 2 * jl + 1], y1);
-            }
-        }
-        if (BASE && c.live) hst[(size_t)jl * Mold] = h0;
-        const float tail[2] = {h0, part == 0 ? 1.0f : 0.0f};
-        stage_cols<1>(reg + 12, tail);
+        if (gq < 3) stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
+        else stage_cols<1>(reg + 12, hp + 24);
     }
     if (!BASE && (n == c.s || n == c.t)) spin_n = 1 - spin_n;
     if (part == 1 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
@@ -585,7 +571,7 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
 #pragma unroll
     for (int j = 0; j < kUP; ++j) { hA[j] = 0.f; hB[j] = 0.f; hC[j] = 0.f; }
     if (!BASE && c.live) {   // restart from the base states after site s: hA <- top layer, hB <- the layer below, ...
-        const float* src = a.hstore + ((c.rowbase + s) * L * (size_t)H + kUP * part) * Mold + c.m;
+        const float* src = a.hstore + ((c.rowbase + s) * L * (size_t)H + kPU * part) * Mold + c.m;
 #pragma unroll
         for (int j = 0; j < kUP; ++j) {
             hA[j] = src[((size_t)(L - 1) * H + j) * Mold];
@@ -593,11 +579,10 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
             if (L > 2) hC[j] = src[(size_t)j * Mold];
         }
     }
-    const float one = part == 0 ? 1.0f : 0.0f;
-    const uint32_t regp = c.lane_addr + kColR + 16 * part;
-    stage_all(regp + 64 * (L - 1), hA, one);
-    if (L > 1) stage_all(regp + 64 * (L - 2), hB, one);
-    if (L > 2) stage_all(regp, hC, one);
+    const uint32_t regp = c.lane_addr + kColR + (kPU / 2) * part;
+    stage_all(regp + 64 * (L - 1), hA);
+    if (L > 1) stage_all(regp + 64 * (L - 2), hB);
+    if (L > 2) stage_all(regp, hC);
     c.pn = -1;
     c.nup = 0;
     if (part == 0) {
@@ -650,7 +635,7 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
 }
 
 // the MMA instructions of one (site, layer) step; executed by every lane of the (converged) MMA warp, one elected lane issues.
-// x group: D[junk | cx | r | u] = x * X^T (overwrite), h group: D[r | u | ch | junk] += h * H^T, where the very first h
+// x group: D[cx | r | u | 4] = x * X^T (overwrite), h group: D[r | u | ch | junk] += h * H^T, where the very first h
 // instruction is split in two because it accumulates onto r, u but must overwrite ch.  Consecutive instructions reuse the A chunk
 // where they can (hi x B_hi, hi x B_lo, then lo x B_hi).
 __device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t rH, uint32_t x_hi, uint32_t x_lo, uint32_t h_hi, uint32_t h_lo,
@@ -659,11 +644,11 @@ __device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t
     constexpr uint32_t idRU = (1u << 4) | ((uint32_t)(kNRU >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t idC = (1u << 4) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dX = tbase + kColX, dH = tbase + kColRU, dCH = tbase + kColCH;
-    if (k16) {   // one-hot input: exact in FP16, no low limb; the x images start one row group (8 rows x 32 bytes) early
-        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_hi - 256, 128, 2 * 128), idAll, 0);
-        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_lo - 256, 128, 2 * 128), idAll, 1);
+    if (k16) {   // one-hot input: exact in FP16, no low limb
+        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_hi, 128, 2 * 128), idAll, 0);
+        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_lo, 128, 2 * 128), idAll, 1);
     } else {
-        const uint64_t bhi = umma::smem_desc(x_hi - kKC * 128, 128, kKC * 128), blo = umma::smem_desc(x_lo - kKC * 128, 128, kKC * 128);
+        const uint64_t bhi = umma::smem_desc(x_hi, 128, kKC * 128), blo = umma::smem_desc(x_lo, 128, kKC * 128);
 #pragma unroll
         for (int ks = 0; ks < kKp / 16; ++ks) {
             umma::mma_f16_ts_elect(dX, rX + ks * 8, bhi + (uint64_t)(ks * 16), idAll, ks > 0);
@@ -823,6 +808,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         for (uint32_t c = 0; c < (uint32_t)(64 * L + 8); c += 8) umma::tmem_st8(lane_addr + kColR + c, z);
         const float one[1] = {__uint_as_float(pack_h2(1.0f, 0.0f))};
         umma::tmem_st1(lane_addr + kColR + 64 * L + 1, one);               // one-hot region: k = 2 is the constant 1
+        for (int l = 0; l < L; ++l) umma::tmem_st1(lane_addr + kColR + 64 * l + kKOne / 2, one);   // state regions: k = 50 (nothing else writes it)
         umma::wait_st();
     }
     if (is_row) umma::mbar_wait(&bars[kWImg], 0);                           // tab is read with ordinary loads
