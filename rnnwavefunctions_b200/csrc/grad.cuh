@@ -856,7 +856,7 @@ static int launch_wgrad(const GruLayout& g, const GradWs<T>& w, int M, int64_t n
     a.ksplit = w.ksplit;
     bool fast = false;
     if constexpr (std::is_same<T, float>::value) {
-        if (!head && wgtc::supported(R, a.cols, M) && !getenv("RNNWF_WGRAD_FFMA")) {
+        if (wgtc::supported(R, a.cols, M) && !getenv("RNNWF_WGRAD_FFMA")) {   // layers and the head alike
             fast = true;
             const wgtc::Geo q = wgtc::make_geo(R, a.cols, M);
             auto k = wgtc::wgrad_kernel;
