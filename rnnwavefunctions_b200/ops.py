@@ -80,6 +80,8 @@ def as_u8_samples(samples, device, n_sites):
     t = t.reshape(t.shape[0], -1)
     if t.shape[1] != n_sites:
         raise ValueError(f"samples have {t.shape[1]} sites, model has {n_sites}")
+    if t.device.type == "cpu" and t.dtype != torch.uint8:
+        t = t.to(torch.uint8)            # narrow on the host: one byte per site crosses PCIe, not the reference's int64
     return t.to(device=device, dtype=torch.uint8, non_blocking=True).contiguous()
 
 
