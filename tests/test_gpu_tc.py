@@ -104,3 +104,18 @@ def test_ragged_sample_counts_local_energies_and_gradient(ns):
     want = TG.gru_vmc_grad({k: v.astype(np.float64) for k, v in p.items()}, s, w)
     err = np.linalg.norm(got - want) / np.linalg.norm(want)
     assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("L", [1, 2, 3])
+@pytest.mark.parametrize("N", [2, 3, 4, 5])
+def test_shortest_chains(L, N):
+    """Chains of 0..4 sites: the triangles at both ends of the anti-diagonal order have no full diagonal between them."""
+    p = O.randomize_biases(O.init_gru_params([50] * L, seed=3 + L, dtype=np.float32, scale=2.0), seed=N)
+    model = ops.make_model(num_layers=L, units=50, n_sites=N)
+    flat = torch.tensor(O.flatten(p), device=dev())
+    s = O.all_configs(N)
+    Jz = np.ones(N)
+    e, lp = ops.tfim_eloc(model, flat, u8(s), Jz, 0.7)
+    ref = O.ising_local_energies(Jz, 0.7, s, lambda c: O.log_probability(p, c))
+    np.testing.assert_allclose(e.cpu().numpy(), ref, rtol=1e-5)
+    np.testing.assert_allclose(np.exp(lp.cpu().numpy()).sum(), 1.0, rtol=1e-5)      # all 2^N configurations: normalised
