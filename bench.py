@@ -263,8 +263,20 @@ def run_b200_arm(args):
             peaks = json.load(f)
     except Exception:
         pass
+    # DRAM traffic of the dominant kernel per launch: one recorded ncu capture of this workload (profiles/chain_kernel_traffic.json)
+    traffic, traffic_note = None, "no ncu capture recorded for this workload"
+    try:
+        with open(os.path.join(ROOT, "profiles", "chain_kernel_traffic.json")) as f:
+            tj = json.load(f)
+        wl = tj["workload"]
+        if (wl["n_sites"], wl["layers"], wl["units"], wl["samples_per_gpu"], bool(wl["parity"])) == (N, LAYERS, UNITS, ns, bool(args.parity)) \
+                and ops.tfim_chain_mode(wf.model) == 3:
+            traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+            traffic_note = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), recorded ncu capture: " + tj["how"]
+    except Exception:
+        pass
     common = {"achieved": achieved, "unit": "TFLOP/s", "kernel_ms": chain_ms, "kernel_share_of_step": dom_ms / t_ms, "launches_timed": dom_n,
-              "flops_per_launch": chain_flops, "traffic": None, "fp32_ffma_peak_measured": ffma_meas,
+              "flops_per_launch": chain_flops, "traffic": traffic, "traffic_note": traffic_note, "fp32_ffma_peak_measured": ffma_meas,
               "fp32_ffma_peak_theoretical": FP32_PEAK_THEORETICAL_TFLOPS, "achieved_over_fp32_ffma_peak": achieved / ffma_meas,
               "step_algorithmic_tflops": step_flops * args.steps / (t_ms * 1e-3) / 1e12}
     if mode == 0:
