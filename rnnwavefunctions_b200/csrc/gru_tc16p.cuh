@@ -52,6 +52,9 @@
 #ifndef RNNWF_UNROLL3
 #define RNNWF_UNROLL3 1
 #endif
+#ifndef RNNWF_LATE_HEAD
+#define RNNWF_LATE_HEAD 1
+#endif
 
 namespace rnnwf {
 namespace tc16p {
@@ -340,11 +343,15 @@ template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(cons
 // probability head without FP64: log-softmax term of the pending top-layer step in FP32 (log1pf / expf, ~1e-7 relative, the same
 // numbers finish_head casts to double), accumulated with Kahan compensation.  FLIP: term - base term, both FP32 numbers of nearly
 // equal magnitude, so the difference is (almost always) exact.
-template <bool BASE> __device__ __forceinline__ void finish_head_f32(const Args& a, Ctx& c) {
+// LATE: called two steps after the top-layer step instead of one.  Its c_done phase is then two phases back -- a parity wait on it
+// would alias the phase in progress -- and the wait is not needed: this thread has passed the commit barrier of the current step,
+// whose MMAs were issued after every row thread had released the accumulators of the step before, i.e. after every c_done arrival
+// of the top-layer step (the barrier chain carries the acquire of part 1's zsm store).
+template <bool BASE, bool LATE = false> __device__ __forceinline__ void finish_head_f32(const Args& a, Ctx& c) {
     if (c.pn < 0) return;
     const int pn = c.pn, psg = c.psg;
     c.pn = -1;
-    umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
+    if (!LATE) umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
     if (!c.live) return;
     const float4 o = c.zsm[c.pbuf * kRows + c.rowi];
     const float f0 = c.pz.x + o.x + c.tab[128], f1 = c.pz.y + o.y + c.tab[129];
@@ -454,7 +461,12 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     umma::mbar_arrive(&c.bars[kAccFree]);              // the accumulators may be overwritten by the next step's MMAs
     TCP_T(long long t2 = clock64(); c.w_c += t2 - t1;)
     if (part == 0) {
+        // the pending head of the last top-layer step.  Three-layer copies: finished in the bottom-layer step, the shortest of the
+        // three and the one the top layer's MMAs run under (ncu: the top-layer copy waited 11 % of its time at the commit barrier);
+        // the middle-layer step only takes it when no bottom-layer step follows on this anti-diagonal (the last two of a chain)
         if constexpr (CPLX) finish_head<BASE, CPLX>(a, c);
+        else if constexpr (LS == 0 && RNNWF_LATE_HEAD) finish_head_f32<BASE, true>(a, c);
+        else if constexpr (LS == 1 && RNNWF_LATE_HEAD) { if (n + 1 >= N) finish_head_f32<BASE>(a, c); }
         else finish_head_f32<BASE>(a, c);
     }
     // ---- reset / update gates (see ru_pair).  RNNWF_FUSED: the gates of a unit pair are computed right before its candidate, so
