@@ -33,8 +33,26 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _on_device_of(index):
+    """Decorator: run the wrapped C-ABI call with the CUDA device of positional argument `index` current (the
+    library launches on the current device and on the current stream of that device), so wave functions built
+    with device='cuda:1' work while another device is current."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*args, **kw):
+            t = args[index]
+            if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                raise ValueError(f"{fn.__name__}: argument {index} must be a CUDA tensor")
+            with torch.cuda.device(t.device):
+                return fn(*args, **kw)
+        return wrapped
+    return deco
 
 
 class _Workspace:
@@ -85,6 +103,7 @@ def as_u8_samples(samples, device, n_sites):
     return t.to(device=device, dtype=torch.uint8, non_blocking=True).contiguous()
 
 
+@_on_device_of(1)
 def sample(model, params, ns, seed=0, sample_offset=0):
     """-> uint8 [ns, N] on params.device."""
     _check_params(model, params)
@@ -95,6 +114,7 @@ def sample(model, params, ns, seed=0, sample_offset=0):
     return out
 
 
+@_on_device_of(1)
 def logpsi(model, params, samples_u8, flags=0):
     """-> float64 [ns] (probability head) or complex128 [ns] (complex head)."""
     _check_params(model, params)
@@ -106,6 +126,7 @@ def logpsi(model, params, samples_u8, flags=0):
     return torch.view_as_complex(out) if cplx else out
 
 
+@_on_device_of(1)
 def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
     _check_params(model, params)
     ns = samples_u8.shape[0]
@@ -118,6 +139,7 @@ def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
     return eloc, logp
 
 
+@_on_device_of(1)
 def tfim_flip_ratios(model, params, samples_u8, jz, bx, flags=0):
     """-> (eloc [ns], logp [ns], ratios [ns, N]) with ratios[s, k] = psi(sigma_s, site k flipped) / psi(sigma_s) (rnnwf_tfim_flip_ratios)."""
     _check_params(model, params)
@@ -137,6 +159,7 @@ def tfim_chain_mode(model) -> int:
     return int(_lib.load().rnnwf_tfim_chain_mode(C.byref(model)))
 
 
+@_on_device_of(1)
 def tfim_diag(model, samples_u8, jz):
     ns = samples_u8.shape[0]
     jz = torch.as_tensor(jz, dtype=torch.float64).reshape(-1).to(samples_u8.device).contiguous()
@@ -145,6 +168,7 @@ def tfim_diag(model, samples_u8, jz):
     return out
 
 
+@_on_device_of(0)
 def tfim_enumerate(samples_u8):
     ns, N = samples_u8.shape
     out = torch.empty((N + 1, ns, N), dtype=torch.int32, device=samples_u8.device)
@@ -152,6 +176,7 @@ def tfim_enumerate(samples_u8):
     return out
 
 
+@_on_device_of(0)
 def j1j2_enumerate(samples_u8, j1, j2, bz, periodic=False, marshall_sign=False, want_sigmas=True):
     ns, N = samples_u8.shape
     dev = samples_u8.device
@@ -165,6 +190,7 @@ def j1j2_enumerate(samples_u8, j1, j2, bz, periodic=False, marshall_sign=False, 
     return sig, el, cnt
 
 
+@_on_device_of(1)
 def j1j2_eloc(model, params, samples_u8, j1, j2, bz, marshall_sign=False, want_logpsi=True):
     _check_params(model, params)
     ns = samples_u8.shape[0]
@@ -178,6 +204,7 @@ def j1j2_eloc(model, params, samples_u8, j1, j2, bz, marshall_sign=False, want_l
     return torch.view_as_complex(eloc), (torch.view_as_complex(lpsi) if want_logpsi else None)
 
 
+@_on_device_of(1)
 def vmc_grad(model, params, samples_u8, weights, flags=0):
     """weights: float64 [ns] (probability head) or complex128 / float64 [ns,2] (complex head). -> float64 [P]."""
     _check_params(model, params)
@@ -193,11 +220,13 @@ def vmc_grad(model, params, samples_u8, weights, flags=0):
     return grad
 
 
+@_on_device_of(1)
 def adam_step(model, theta, mom, vel, grad, t, lr, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
     check(_lib.load().rnnwf_adam_step(model.dtype, theta.numel(), _ptr(theta), _ptr(mom), _ptr(vel), _ptr(grad), float(grad_scale),
                                       float(lr), beta1, beta2, eps, int(t), _stream()))
 
 
+@_on_device_of(0)
 def energy_moments(eloc_f64, stride=1, count=None):
     """-> float64 [3] = (sum, sum of squares, n) over eloc_f64[0], eloc_f64[stride], ... (count entries)."""
     ns = eloc_f64.numel() // stride if count is None else int(count)
@@ -225,6 +254,7 @@ def ffma_peak(iters=20000):
     return out.value
 
 
+@_on_device_of(0)
 def umma_selftest(a, b, passes=3, f16=False, dcol=0):
     """d = a @ b.T on the tcgen05 path (a [128,K], b [N,K] float32 CUDA tensors); f16: FP16 hi/lo operands."""
     n, k = b.shape

@@ -98,3 +98,17 @@ def join_named(named, shapes, dtype):
             raise ValueError(f"{name}: shape {a.shape} != {shape}")
         parts.append(a.reshape(-1))
     return np.concatenate(parts).astype(dtype)
+
+
+def units_from_named(named, scope=SCOPE):
+    """Layer widths of a GRU stack from a `{variable name: array}` dump (names with or without TF's ':0' suffix)."""
+    units = []
+    while True:
+        key = f"{scope}/multi_rnn_cell/cell_{len(units)}/cudnn_compatible_gru_cell/gates/bias"
+        a = named.get(key, named.get(key + ":0"))
+        if a is None:
+            break
+        units.append(int(np.asarray(a).shape[0]) // 2)
+    if not units:
+        raise KeyError(f"no {scope}/multi_rnn_cell/cell_0/... variables in the dump")
+    return units

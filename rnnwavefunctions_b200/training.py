@@ -145,7 +145,7 @@ def _units_ending(units):
 
 def _run(wf, hamiltonian, numsteps, numsamples, lr_of_it, numsamples_tag, save_prefix, mean_name, var_name, ckpt_name,
          save, verbose, resume, complex_energy=False):
-    """The loop of :199-227: sample -> E_loc -> record -> (checkpoint) -> Adam step -> (save energies)."""
+    """The loop of :199-227: sample -> E_loc -> record -> Adam step -> (checkpoint) -> (save energies)."""
     opt = VMC(wf, hamiltonian, numsamples)
     rank0 = opt.rank == 0
     meanEnergy, varEnergy = [], []
@@ -166,11 +166,13 @@ def _run(wf, hamiltonian, numsteps, numsamples, lr_of_it, numsamples_tag, save_p
         varEnergy.append(varE)
         if it % 10 == 0 and verbose and rank0:
             print("mean(E): {0}, var(E): {1}, #samples {2}, #Step {3} \n\n".format(meanE, varE, numsamples_tag, it))
-        if save and rank0 and it % 500 == 0:
-            sd = opt.state_dict()
-            np.savez(ck, meanEnergy=np.asarray(meanEnergy), varEnergy=np.asarray(varEnergy), **sd, **wf.named_parameters())
         g = opt.gradient(samples, eloc, mean, n)
         opt.apply(g, lr_of_it(it))
+        if save and rank0 and it % 500 == 0:
+            # written AFTER update `it` (the reference's Saver runs before the optstep, :217-221, but it never resumes):
+            # the file holds the parameters that iteration it+1 starts from, so a resumed run replays nothing and skips nothing
+            sd = opt.state_dict()
+            np.savez(ck, meanEnergy=np.asarray(meanEnergy), varEnergy=np.asarray(varEnergy), **sd, **wf.named_parameters())
         if save and rank0 and it % 10 == 0:
             np.save(os.path.join(save_prefix, mean_name), meanEnergy)
             np.save(os.path.join(save_prefix, var_name), varEnergy)

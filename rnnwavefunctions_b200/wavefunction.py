@@ -226,5 +226,8 @@ class ComplexRNNwavefunction(_WavefunctionBase):
         return self.log_amplitudes
 
 
+units_from_named = P.units_from_named
+
+
 # The reference gives every class the same name, selected by which directory is on sys.path.
 RNNwavefunction = RNNwavefunction1D

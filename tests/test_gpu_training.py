@@ -97,6 +97,9 @@ def test_run_1dtfim_converges_to_exact(tmp_path, golden):
     E2, _ = TR.run_1DTFIM(numsteps=520, systemsize=10, num_units=10, Bx=1, num_layers=1, numsamples=500, learningrate=1e-2, seed=111,
                           checkpoint_dir=str(tmp_path), verbose=False, resume=True)
     assert len(E2) == 521 and np.allclose(E2[:501], E[:501])
+    # the checkpoint is written after update 500, so the resumed trajectory is the uninterrupted one (same Philox draws,
+    # same Adam state): iterations 501..520 must reproduce the first run, which a skipped update would break
+    np.testing.assert_allclose(E2[501:521], E[501:521], rtol=1e-9, atol=1e-9)
 
 
 def test_run_1dtfim_tensor_core_path_converges(tmp_path):
