@@ -55,6 +55,12 @@
 #ifndef RNNWF_LATE_HEAD
 #define RNNWF_LATE_HEAD 1
 #endif
+#ifndef RNNWF_EX2POLY
+#define RNNWF_EX2POLY 0   // number of unit pairs (of 13 per row thread) whose candidate 2^a runs on the FMA pipe (ex2_poly2) instead of MUFU
+#endif
+#ifndef RNNWF_KPACK
+#define RNNWF_KPACK 1     // 3e: the three split passes packed densely along K (10 MMAs of K = 16 per operand group instead of 12)
+#endif
 
 namespace rnnwf {
 namespace tc16p {
@@ -84,6 +90,28 @@ __device__ __forceinline__ f2_t neg_rcp2(float a, float b) {
 }
 __device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+// (2^a0, 2^a1) on the FMA pipe: round to the nearest integer with the 1.5 * 2^23 trick, degree-5 minimax polynomial of 2^f on
+// [-0.5, 0.5] in packed FP32 (relative error 2.3e-7, the same as ex2.approx), exponent added to the result's bits.  The XU pipe
+// (16 lanes per SM) is the busiest pipe of the chain kernel (ncu: 72 %); each pair moved here frees 16 XU cycles per warp for
+// about 12 issue slots.  Inputs are clamped to [-125, 126] (2^126 + 1 and 2^-125 + 1 give the saturated gate values).
+__device__ __forceinline__ f2_t ex2_poly2(float a0, float a1) {
+    a0 = fminf(fmaxf(a0, -125.f), 126.f);
+    a1 = fminf(fmaxf(a1, -125.f), 126.f);
+    const f2_t a = f2_make(a0, a1), magic = f2_make(12582912.f, 12582912.f);
+    const f2_t t = f2_add(a, magic);
+    const f2_t f = f2_sub(a, f2_sub(t, magic));
+    f2_t p = f2_fma(f2_make(0x1.5c08ccp-10f, 0x1.5c08ccp-10f), f, f2_make(0x1.3d0c52p-7f, 0x1.3d0c52p-7f));
+    p = f2_fma(p, f, f2_make(0x1.c6b6e6p-5f, 0x1.c6b6e6p-5f));
+    p = f2_fma(p, f, f2_make(0x1.ebf918p-3f, 0x1.ebf918p-3f));
+    p = f2_fma(p, f, f2_make(0x1.62e428p-1f, 0x1.62e428p-1f));
+    p = f2_fma(p, f, f2_make(0x1.000002p+0f, 0x1.000002p+0f));
+    float p0, p1, t0, t1;
+    f2_split(p, p0, p1);
+    f2_split(t, t0, t1);
+    return f2_make(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)),
+                   __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
+}
+
 constexpr int kRows = 128, kRowThreads = 256, kThreads = 384, kMmaWarp = 8;   // warps 9-11 only complete the MMA warp's warpgroup (setmaxnreg)
 constexpr int kUP = 26, kPU = 24;                        // units per row thread; first unit of part 1: part p owns units [24 p, 24 p + 26),
                                                          // units 24 and 25 are computed (identically) by both threads of a sample, so that
@@ -93,7 +121,20 @@ constexpr int kNAll = 160, kNRU = 112, kNC = 64;         // N of the merged inst
 constexpr int kRowsImg = 160;                            // stored B rows of an image: three gate blocks + 4 zero rows
 constexpr int kKp = 64, kKC = 8;                         // K padded to 4 MMA steps of 16; 16-byte chunks per row
 constexpr int kColX = 0, kColCX = 0, kColRU = 52, kColCH = 156, kColR = 224;   // kColX: D base of the x group (cx | r | u)
-constexpr int kKOne = 50;                                // K index of the constant-1 (bias) column
+#if RNNWF_KPACK
+// Generation 3e, dense K packing.  Operand region (56 columns = K 112): columns 0..24 hi halves of units 0..49, column 25 a second
+// copy of hi(48, 49), column 26 the constant (1, 1), column 27 zero, columns 28..52 lo halves of units 0..49, 53..55 zero.
+// Image B1 (K = 64, 8 core-matrix columns c0..c7): c0..c5 = W_hi of units 0..47; c6 = W_hi[48], W_hi[49], W_lo[48], W_lo[49], b_hi,
+// b_lo, 0, 0; c7 = a copy of c0.  Image B2 (K = 48): W_lo of units 0..47.  The MMA of operand chunk q (columns 8q..8q+7) takes the
+// B1 core columns (0,1) (2,3) (4,5) (6,7) (1,2) (3,4) (5,6) for q = 0..6 -- a descriptor start may sit on any core column -- which
+// pairs hi(0..49) with W_hi, the copy of hi(48,49) with W_lo, the constant with the two halves of the bias and lo(0..49) with W_hi;
+// chunks 0..2 run a second time against B2: hi(0..47) x W_lo.  7 + 3 = 10 instructions of K = 16 carry the 152 products
+// per output that 3 x 64 = 12 carried before.
+constexpr int kLoCol = 28, kOneCol = 26, kK2 = 48, kKC2 = 6;
+#else
+constexpr int kLoCol = 32;
+#endif
+constexpr int kKOne = 50;                                // K index of the constant-1 (bias) column (unpacked layout)
 enum { kFull = 0, kAccFree = 1, kCDone = 2, kWImg = 3, kNumBars = 4 };
 
 __host__ __device__ __forceinline__ int unit_of_col(int c) { return c < 50 ? c : -1; }   // gate-block column -> unit
@@ -102,6 +143,7 @@ __host__ __device__ __forceinline__ int unit_of_k(int k) { return k < 50 ? k : -
 struct Layout {
     int L, H, N;
     int im_bytes, im0_bytes;                      // one precision half of an image with K = 64 / K = 16 (layer 0 input)
+    int im2_bytes;                                // second image of an operand (KPACK: B2 with K = 48; else the lo half, K = 64)
     int l0_bytes, l1_bytes;
     int tab_off, tab_floats, img_bytes;
 };
@@ -111,8 +153,13 @@ inline Layout make_layout(const GruLayout& g) {
     t.L = g.L; t.H = g.H; t.N = g.N;
     t.im_bytes = kRowsImg * kKp * 2;
     t.im0_bytes = kRowsImg * 16 * 2;
-    t.l0_bytes = 2 * t.im_bytes + 2 * t.im0_bytes;
-    t.l1_bytes = 4 * t.im_bytes;
+#if RNNWF_KPACK
+    t.im2_bytes = kRowsImg * kK2 * 2;
+#else
+    t.im2_bytes = t.im_bytes;
+#endif
+    t.l0_bytes = t.im_bytes + t.im2_bytes + 2 * t.im0_bytes;
+    t.l1_bytes = 2 * (t.im_bytes + t.im2_bytes);
     t.tab_off = t.l0_bytes + (g.L - 1) * t.l1_bytes;
     t.tab_floats = g.nheads * (2 * 64 + 4);       // per head: Wd[64][2] | bd[2] | pad
     t.img_bytes = t.tab_off + t.tab_floats * 4;
@@ -133,9 +180,33 @@ inline bool supported(const GruLayout& g) {
 // -log2(e), candidate rows by 2 log2(e); the constant-1 K column carries the biases bg (h part of r, u), bch (h part of the
 // candidate) and bci (x part of the candidate).  Layer 0: the x images have K = 16 with the two one-hot rows of the input kernels
 // at k = 0, 1 and bci at k = 2.
+// scaled weight of output row n (gate-block layout) of the h image (xpart = 0: [r | u | ch]) or the x image (xpart = 1: [cx | r | u])
+// of layer l for input unit ku in [0, 50), or the bias that rides on the constant-1 column for ku == 50
+__device__ __forceinline__ float packed_weight(const GruLayout& g, const float* __restrict__ flat, int l, int xpart, int n, int ku) {
+    const int H = g.H, d = g.d[l];
+    const float kS = -1.4426950408889634f, kC = 2.8853900817779268f;
+    const float* Kg = flat + g.flat_off[l];
+    const float* bg = Kg + (d + H) * 2 * H;
+    const float* Kci = bg + 2 * H;
+    const float* Kch = Kci + d * H;
+    const float* bci = Kch + H * H;
+    const float* bch = bci + H;
+    const int blk = n / kBW;
+    const int j = blk < 3 ? unit_of_col(n % kBW) : -1;       // output unit of this row (-1: padding)
+    if (j < 0 || ku < 0 || ku > H) return 0.f;
+    const bool cand = xpart ? blk == 0 : blk == 2;
+    const int gate = xpart ? blk - 1 : blk;                  // 0: r, 1: u (unused for the candidate block)
+    if (!xpart) {
+        if (!cand) return ku < H ? kS * Kg[(d + ku) * 2 * H + gate * H + j] : kS * bg[gate * H + j];
+        return ku < H ? kC * Kch[ku * H + j] : kC * bch[j];
+    }
+    if (ku < H && ku >= d) return 0.f;                       // layer 0: only the two one-hot rows exist
+    if (!cand) return ku < H ? kS * Kg[ku * 2 * H + gate * H + j] : 0.f;
+    return ku < H ? kC * Kci[ku * H + j] : kC * bci[j];
+}
+
 __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ flat, unsigned char* __restrict__ img) {
     const int H = g.H;
-    const float kS = -1.4426950408889634f, kC = 2.8853900817779268f;
     const int per_l = 2 * kRowsImg * kKp;               // h image + x image
     const int total = g.L * per_l;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -144,51 +215,40 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         const int xpart = q / (kRowsImg * kKp);
         q %= kRowsImg * kKp;
         const int n = q / kKp, k = q % kKp;
-        const int d = g.d[l];
-        const float* Kg = flat + g.flat_off[l];
-        const float* bg = Kg + (d + H) * 2 * H;
-        const float* Kci = bg + 2 * H;
-        const float* Kch = Kci + d * H;
-        const float* bci = Kch + H * H;
-        const float* bch = bci + H;
         unsigned char* Lb = img + (l == 0 ? 0 : t.l0_bytes + (l - 1) * t.l1_bytes);
-        // gate blocks: h image [r | u | ch], x image [cx | r | u]
-        const int blk = n / kBW;
-        const bool cand = xpart ? blk == 0 : blk == 2;
-        const int gate = xpart ? blk - 1 : blk;                  // 0: r, 1: u (unused for the candidate block)
-        const int j = blk < 3 ? unit_of_col(n % kBW) : -1;       // output unit of this row (-1: padding)
-        const int ku = unit_of_k(k);                             // input unit of this K index (-1: constant / padding)
-        float v = 0.f;
-        int KC = kKC;
-        unsigned char *hi_b, *lo_b;
-        if (!xpart) {
-            if (j >= 0) {
-                if (!cand) v = ku >= 0 ? kS * Kg[(d + ku) * 2 * H + gate * H + j] : (k == kKOne ? kS * bg[gate * H + j] : 0.f);
-                else v = ku >= 0 ? kC * Kch[ku * H + j] : (k == kKOne ? kC * bch[j] : 0.f);
-            }
-            hi_b = Lb;
-            lo_b = Lb + t.im_bytes;
-        } else {
-            hi_b = Lb + 2 * t.im_bytes;
-            if (l > 0) {
-                if (j >= 0) {
-                    if (!cand) v = ku >= 0 ? kS * Kg[ku * 2 * H + gate * H + j] : 0.f;
-                    else v = ku >= 0 ? kC * Kci[ku * H + j] : (k == kKOne ? kC * bci[j] : 0.f);
-                }
-                lo_b = hi_b + t.im_bytes;
-            } else {
-                if (k >= 16) continue;
-                KC = 2;
-                if (j >= 0) {
-                    if (!cand) v = k < 2 ? kS * Kg[k * 2 * H + gate * H + j] : 0.f;
-                    else v = k < 2 ? kC * Kci[k * H + j] : (k == 2 ? kC * bci[j] : 0.f);
-                }
-                lo_b = hi_b + t.im0_bytes;
-            }
+        __half* im1 = reinterpret_cast<__half*>(Lb + (xpart ? t.im_bytes + t.im2_bytes : 0));
+        if (xpart && l == 0) {                          // one-hot input: K = 16, rows k = 0, 1 of the input kernels, bci at k = 2
+            if (k >= 16) continue;
+            const float v = k < 2 ? packed_weight(g, flat, 0, 1, n, k) : (k == 2 ? packed_weight(g, flat, 0, 1, n, H) : 0.f);
+            const __half hi = __float2half_rn(v);
+            im1[core_off(n, k, 2)] = hi;
+            reinterpret_cast<__half*>(Lb + t.im_bytes + t.im2_bytes + t.im0_bytes)[core_off(n, k, 2)] = __float2half_rn(v - __half2float(hi));
+            continue;
         }
+        __half* im2 = reinterpret_cast<__half*>(Lb + (xpart ? t.im_bytes + t.im2_bytes : 0) + t.im_bytes);
+#if RNNWF_KPACK
+        if (k < kK2 + 2) {                               // units 0..49: hi into B1 at k; lo into B2 (units < 48) or B1 at k + 2 (48, 49)
+            const float v = packed_weight(g, flat, l, xpart, n, k);
+            const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+            im1[core_off(n, k, kKC)] = hi;
+            if (k < kK2) im2[core_off(n, k, kKC2)] = lo;
+            else im1[core_off(n, k + 2, kKC)] = lo;
+        } else if (k == 52) {                            // the two halves of the bias against the constant (1, 1)
+            const float v = packed_weight(g, flat, l, xpart, n, H);
+            const __half hi = __float2half_rn(v);
+            im1[core_off(n, 52, kKC)] = hi;
+            im1[core_off(n, 53, kKC)] = __float2half_rn(v - __half2float(hi));
+        } else if (k == 54 || k == 55) {
+            im1[core_off(n, k, kKC)] = __float2half_rn(0.f);
+        } else if (k >= 56) {                            // c7: copy of c0 (W_hi of units 0..7 against the first lo halves)
+            im1[core_off(n, k, kKC)] = __float2half_rn(packed_weight(g, flat, l, xpart, n, k - 56));
+        }
+#else
+        const float v = packed_weight(g, flat, l, xpart, n, k < H ? k : (k == kKOne ? H : -1));
         const __half hi = __float2half_rn(v);
-        reinterpret_cast<__half*>(hi_b)[core_off(n, k, KC)] = hi;
-        reinterpret_cast<__half*>(lo_b)[core_off(n, k, KC)] = __float2half_rn(v - __half2float(hi));
+        im1[core_off(n, k, kKC)] = hi;
+        im2[core_off(n, k, kKC)] = __float2half_rn(v - __half2float(hi));
+#endif
     }
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < t.tab_floats; idx += gridDim.x * blockDim.x) {
         const int hd = idx / 132, r = idx % 132;        // per head: [part][slot (26)][2] weights of unit 24 part + slot | pad | bd[2] at 128 | pad
@@ -203,9 +263,10 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
     }
 }
 
-// (hi, lo) FP16 pairs of 2 * NC consecutive values -> NC operand-region columns (two values per column)
-template <int NC> __device__ __forceinline__ void stage_cols(uint32_t col, const float* h) {
-    float hi[NC], lo[NC];
+// (hi, lo) FP16 pairs of 2 * NC consecutive values -> NC operand-region columns (two values per column).
+// DUP (dense K packing, the column of units 48, 49): hi goes to two adjacent columns (the second one meets W_lo of those units).
+template <int NC, bool DUP = false> __device__ __forceinline__ void stage_cols(uint32_t col, const float* h) {
+    float hi[NC + 1], lo[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         const uint32_t wh = pack_h2(h[2 * c], h[2 * c + 1]);
@@ -221,18 +282,31 @@ template <int NC> __device__ __forceinline__ void stage_cols(uint32_t col, const
     }
     if constexpr (NC == 4) {
         umma::tmem_st4(col, hi);
-        umma::tmem_st4(col + 32, lo);
+        umma::tmem_st4(col + kLoCol, lo);
     } else {
         static_assert(NC == 1, "column groups are 4 wide or the single tail column");
-        umma::tmem_st1(col, hi);
-        umma::tmem_st1(col + 32, lo);
+        if constexpr (DUP) {
+            hi[1] = hi[0];
+            umma::tmem_st2(col, hi);
+        } else {
+            umma::tmem_st1(col, hi);
+        }
+        umma::tmem_st1(col + kLoCol, lo);
     }
 }
+// the 13th column of a row thread: units 24, 25 (part 0) or 48, 49 (part 1; with dense K packing hi is stored twice)
+__device__ __forceinline__ void stage_tail(uint32_t col, const float* h, int part) {
+#if RNNWF_KPACK
+    if (part) stage_cols<1, true>(col, h);
+    else
+#endif
+        stage_cols<1>(col, h);
+}
 // the 26 units of a row thread -> columns [12 part, 12 part + 13) of an operand region
-__device__ __forceinline__ void stage_all(uint32_t reg_part_addr, const float* hp) {
+__device__ __forceinline__ void stage_all(uint32_t reg_part_addr, const float* hp, int part) {
 #pragma unroll
     for (int gq = 0; gq < 3; ++gq) stage_cols<4>(reg_part_addr + 4 * gq, hp + 8 * gq);
-    stage_cols<1>(reg_part_addr + 12, hp + 24);
+    stage_tail(reg_part_addr + 12, hp + 24, part);
 }
 
 struct Args {
@@ -508,7 +582,8 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
             float a0, a1, h0, h1;
             f2_split(f2_fma(f2_make(rr[jl], rr[jl + 1]), f2_make(dq[jl], dq[jl + 1]), f2_make(dc[jl], dc[jl + 1])), a0, a1);
 #if RNNWF_CAND == 2
-            f2_split(f2_add(f2_make(ex2(a0), ex2(a1)), f2_make(1.0f, 1.0f)), a0, a1);
+            if (jl / 2 < RNNWF_EX2POLY) f2_split(f2_add(ex2_poly2(a0, a1), f2_make(1.0f, 1.0f)), a0, a1);
+            else f2_split(f2_add(f2_make(ex2(a0), ex2(a1)), f2_make(1.0f, 1.0f)), a0, a1);
             const f2_t cc = f2_fma(f2_make(-2.0f, -2.0f), f2_make(rcp(a0), rcp(a1)), f2_make(1.0f, 1.0f));
 #elif RNNWF_CAND == 3   // the reciprocals on the FMA pipe
             f2_split(f2_add(f2_make(ex2(fminf(a0, 60.f)), ex2(fminf(a1, 60.f))), f2_make(1.0f, 1.0f)), a0, a1);
@@ -540,7 +615,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
         }
         // region l takes the new state: it is the h operand of (n + 1, l) and the x operand of (n, l + 1), both visited later
         if (gq < 3) stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
-        else stage_cols<1>(reg + 12, hp + 24);
+        else stage_tail(reg + 12, hp + 24, part);
     }
     if (!BASE && (n == c.s || n == c.t)) spin_n = 1 - spin_n;
     if (part == 1 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
@@ -592,9 +667,9 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
         }
     }
     const uint32_t regp = c.lane_addr + kColR + (kPU / 2) * part;
-    stage_all(regp + 64 * (L - 1), hA);
-    if (L > 1) stage_all(regp + 64 * (L - 2), hB);
-    if (L > 2) stage_all(regp, hC);
+    stage_all(regp + 64 * (L - 1), hA, part);
+    if (L > 1) stage_all(regp + 64 * (L - 2), hB, part);
+    if (L > 2) stage_all(regp, hC, part);
     c.pn = -1;
     c.nup = 0;
     if (part == 0) {
@@ -650,27 +725,52 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
 // x group: D[cx | r | u | 4] = x * X^T (overwrite), h group: D[r | u | ch | junk] += h * H^T, where the very first h
 // instruction is split in two because it accumulates onto r, u but must overwrite ch.  Consecutive instructions reuse the A chunk
 // where they can (hi x B_hi, hi x B_lo, then lo x B_hi).
-__device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t rH, uint32_t x_hi, uint32_t x_lo, uint32_t h_hi, uint32_t h_lo,
+__device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t rH, uint32_t x_1, uint32_t x_2, uint32_t h_1, uint32_t h_2,
                                            bool k16) {
     constexpr uint32_t idAll = (1u << 4) | ((uint32_t)(kNAll >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F16 x F16 -> F32, M = 128
     constexpr uint32_t idRU = (1u << 4) | ((uint32_t)(kNRU >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t idC = (1u << 4) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t dX = tbase + kColX, dH = tbase + kColRU, dCH = tbase + kColCH;
     if (k16) {   // one-hot input: exact in FP16, no low limb
-        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_hi, 128, 2 * 128), idAll, 0);
-        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_lo, 128, 2 * 128), idAll, 1);
+        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_1, 128, 2 * 128), idAll, 0);
+        umma::mma_f16_ts_elect(dX, rX, umma::smem_desc(x_2, 128, 2 * 128), idAll, 1);
     } else {
-        const uint64_t bhi = umma::smem_desc(x_hi, 128, kKC * 128), blo = umma::smem_desc(x_lo, 128, kKC * 128);
+#if RNNWF_KPACK
+        // operand chunk q (columns 8 q ..) against B1 from core column 2 q (q <= 3) or 2 q - 7 (q >= 4); chunks 0..2 also against B2
+        const uint64_t b1 = umma::smem_desc(x_1, 128, kKC * 128), b2 = umma::smem_desc(x_2, 128, kKC2 * 128);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            umma::mma_f16_ts_elect(dX, rX + q * 8, b1 + (uint64_t)(q * 16), idAll, q > 0);
+            umma::mma_f16_ts_elect(dX, rX + q * 8, b2 + (uint64_t)(q * 16), idAll, 1);
+        }
+#pragma unroll
+        for (int q = 3; q < 7; ++q) umma::mma_f16_ts_elect(dX, rX + q * 8, b1 + (uint64_t)((q == 3 ? 6 : 2 * q - 7) * 8), idAll, 1);
+#else
+        const uint64_t bhi = umma::smem_desc(x_1, 128, kKC * 128), blo = umma::smem_desc(x_2, 128, kKC * 128);
 #pragma unroll
         for (int ks = 0; ks < kKp / 16; ++ks) {
             umma::mma_f16_ts_elect(dX, rX + ks * 8, bhi + (uint64_t)(ks * 16), idAll, ks > 0);
             umma::mma_f16_ts_elect(dX, rX + ks * 8, blo + (uint64_t)(ks * 16), idAll, 1);
             umma::mma_f16_ts_elect(dX, rX + 32 + ks * 8, bhi + (uint64_t)(ks * 16), idAll, 1);
         }
+#endif
     }
     {
-        const uint64_t bhi = umma::smem_desc(h_hi, 128, kKC * 128), blo = umma::smem_desc(h_lo, 128, kKC * 128);
-        const uint64_t bch = umma::smem_desc(h_hi + 2 * kBW * kKp * 2, 128, kKC * 128);          // candidate rows of H_hi
+        const uint64_t bch = umma::smem_desc(h_1 + 2 * kBW * kKp * 2, 128, kKC * 128);          // candidate rows of the first image
+#if RNNWF_KPACK
+        const uint64_t b1 = umma::smem_desc(h_1, 128, kKC * 128), b2 = umma::smem_desc(h_2, 128, kKC2 * 128);
+        umma::mma_f16_ts_elect(dH, rH, b1, idRU, 1);
+        umma::mma_f16_ts_elect(dCH, rH, bch, idC, 0);
+        umma::mma_f16_ts_elect(dH, rH, b2, idAll, 1);
+#pragma unroll
+        for (int q = 1; q < 3; ++q) {
+            umma::mma_f16_ts_elect(dH, rH + q * 8, b1 + (uint64_t)(q * 16), idAll, 1);
+            umma::mma_f16_ts_elect(dH, rH + q * 8, b2 + (uint64_t)(q * 16), idAll, 1);
+        }
+#pragma unroll
+        for (int q = 3; q < 7; ++q) umma::mma_f16_ts_elect(dH, rH + q * 8, b1 + (uint64_t)((q == 3 ? 6 : 2 * q - 7) * 8), idAll, 1);
+#else
+        const uint64_t bhi = umma::smem_desc(h_1, 128, kKC * 128), blo = umma::smem_desc(h_2, 128, kKC * 128);
         umma::mma_f16_ts_elect(dH, rH, bhi, idRU, 1);
         umma::mma_f16_ts_elect(dCH, rH, bch, idC, 0);
         umma::mma_f16_ts_elect(dH, rH, blo, idAll, 1);
@@ -681,6 +781,7 @@ __device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t
             umma::mma_f16_ts_elect(dH, rH + ks * 8, blo + (uint64_t)(ks * 16), idAll, 1);
             umma::mma_f16_ts_elect(dH, rH + 32 + ks * 8, bhi + (uint64_t)(ks * 16), idAll, 1);
         }
+#endif
     }
 }
 
@@ -749,7 +850,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
                         const bool dep = pn == -1000 || (pn == n && pl == l - 1) || (pn == n - 1 && pl == l);
                         pn = n; pl = l;
                         const uint32_t lb = sB + (l == 0 ? 0u : (uint32_t)(t.l0_bytes + (l - 1) * t.l1_bytes));
-                        const uint32_t h_hi = lb, h_lo = lb + t.im_bytes, x_hi = lb + 2 * t.im_bytes;
+                        const uint32_t h_hi = lb, h_lo = lb + t.im_bytes, x_hi = lb + t.im_bytes + t.im2_bytes;
                         const uint32_t x_lo = x_hi + (l == 0 ? t.im0_bytes : t.im_bytes);
                         const uint32_t rX = tbase + kColR + 64 * (l == 0 ? L : l - 1), rH = tbase + kColR + 64 * l;
                         TCP_T(long long q0 = clock64();)
@@ -820,7 +921,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         for (uint32_t c = 0; c < (uint32_t)(64 * L + 8); c += 8) umma::tmem_st8(lane_addr + kColR + c, z);
         const float one[1] = {__uint_as_float(pack_h2(1.0f, 0.0f))};
         umma::tmem_st1(lane_addr + kColR + 64 * L + 1, one);               // one-hot region: k = 2 is the constant 1
+#if RNNWF_KPACK
+        const float one2[1] = {__uint_as_float(pack_h2(1.0f, 1.0f))};                            // meets (bias_hi, bias_lo) in B1
+        for (int l = 0; l < L; ++l) umma::tmem_st1(lane_addr + kColR + 64 * l + kOneCol, one2);   // state regions (nothing else writes it)
+#else
         for (int l = 0; l < L; ++l) umma::tmem_st1(lane_addr + kColR + 64 * l + kKOne / 2, one);   // state regions: k = 50 (nothing else writes it)
+#endif
         umma::wait_st();
     }
     if (is_row) umma::mbar_wait(&bars[kWImg], 0);                           // tab is read with ordinary loads
