@@ -17,7 +17,7 @@
  *     1DTFIM/RNNwavefunction.py:72).  2-D RNN samples are uint8 [ns, Nx, Ny] indexed [b][x][y]
  *     (2DTFIM_2DRNN/RNNwavefunction.py:116).
  *   - Parameters are one flat buffer (float or double according to model.dtype) in TF-variable
- *     creation order (see rnnwf_param_layout(); names in rnnwavefunctions_b200/params.py).
+ *     creation order (names, shapes and order: rnnwavefunctions_b200/params.py).
  */
 #ifndef RNNWF_H
 #define RNNWF_H
@@ -157,6 +157,10 @@ int rnnwf_profile_end(int64_t* launches_out, int64_t* dominant_launches_out, dou
 /* FP32 FFMA throughput of the device (TFLOP/s) measured with a register-resident FMA kernel on `stream`:
  * the denominator of the compute roofline the recurrence kernels are held against.        */
 int rnnwf_ffma_peak(int iters, double* tflops_out, void* stream);
+
+/* FP64 throughput of the device (TFLOP/s): mode 0 = DFMA (CUDA cores), mode 1 = mma.sync.m8n8k4.f64 (DMMA).  The roofline
+ * denominators of the float64 models (2DTFIM_1DRNN/RNNwavefunction.py:26-38, 2DTFIM_2DRNN/MDRNNcell.py:21-35 are float64). */
+int rnnwf_fp64_peak(int mode, int iters, double* tflops_out, void* stream);
 
 /* Known-answer check of the tcgen05 / TMEM plumbing the tensor-core recurrence kernels are built on:
  * d[128][n] = a[128][k] * b[n][k]^T on one CTA (A staged in TMEM, B in shared memory, `passes` = 1: TF32, 3: 3xTF32;

@@ -50,6 +50,7 @@ _SIGNATURES = {
     "rnnwf_profile_begin": (C.c_int, []),
     "rnnwf_profile_end": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rnnwf_ffma_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), _P]),
+    "rnnwf_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), _P]),
     "rnnwf_umma_selftest": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)

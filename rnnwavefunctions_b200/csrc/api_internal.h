@@ -52,6 +52,7 @@ int umma_selftest_impl(int N, int K, const float* A, const float* B, float* D, i
 int adam_step_impl(int dtype, int64_t n, void* theta, void* mom, void* vel, const double* grad, double grad_scale, double lr,
                    double b1, double b2, double eps, int64_t t, cudaStream_t s);
 int ffma_peak_impl(int iters, double* tflops, cudaStream_t s);
+int fp64_peak_impl(int mode, int iters, double* tflops, cudaStream_t s);
 int energy_moments_impl(const double* eloc, int64_t ns, int stride, double* stats, cudaStream_t s);
 
 }  // namespace rnnwf

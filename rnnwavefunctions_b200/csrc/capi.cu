@@ -202,6 +202,11 @@ RNNWF_API int rnnwf_ffma_peak(int iters, double* tflops_out, void* stream) {
     return ffma_peak_impl(iters, tflops_out, (cudaStream_t)stream);
 }
 
+RNNWF_API int rnnwf_fp64_peak(int mode, int iters, double* tflops_out, void* stream) {
+    RNNWF_CHECK((mode == 0 || mode == 1) && iters > 0 && tflops_out, -1, "bad arguments to rnnwf_fp64_peak");
+    return fp64_peak_impl(mode, iters, tflops_out, (cudaStream_t)stream);
+}
+
 RNNWF_API int rnnwf_umma_selftest(int n, int k, const float* a, const float* b, float* d, int passes, void* stream) {
     RNNWF_CHECK(a && b && d, -1, "bad arguments to rnnwf_umma_selftest");
     if (passes < 0) return umma_selftest_f16_impl(n, k, a, b, d, (-passes) & 3, (-passes) >> 2, (cudaStream_t)stream);

@@ -803,7 +803,8 @@ template <typename T> static GruLaunch fwd_launch_for(const GruLayout& g, const 
     c.CT = b.CT; c.RT = b.RT; c.M = b.M; c.Mp = b.Mp; c.NTc = b.NT;
     size_t with_w = (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) + (size_t)g.L * g.H * b.M * sizeof(T) + 2 * (size_t)b.Mp + 64;
     c.w_smem = with_w <= (size_t)kSmemLimit;
-    c.smem_bytes = (int)(c.w_smem ? with_w : (size_t)g.L * g.H * b.M * sizeof(T) + 2 * (size_t)b.Mp + 64);
+    c.ring_kc = c.w_smem ? 0 : kRingKC;       // weights that do not fit are streamed through the shared-memory ring (gru_engine.cuh)
+    c.smem_bytes = (int)(c.w_smem ? with_w : (size_t)g.L * g.H * b.M * sizeof(T) + 2 * (size_t)b.Mp + 64 + 2 * (size_t)kRingKC * g.CT * 6 * sizeof(T) + 16);
     return c;
 }
 

@@ -416,7 +416,7 @@ template int gru_tfim_eloc_t<double>(const rnnwf_model&, const void*, const uint
                                      double*, double*, void*, size_t, cudaStream_t);
 
 int tfim_chain_mode_impl(const rnnwf_model& m) {
-    if (m.cell != RNNWF_CELL_GRU || m.dtype != RNNWF_F32 || m.head != RNNWF_HEAD_PROB) return 0;
+    if (m.cell != RNNWF_CELL_GRU || m.dtype != RNNWF_F32) return 0;   // complex head: the J1-J2 exchange chains make the same choice (j1j2.cuh)
     return chain_mode(make_gru_layout(m));
 }
 

@@ -70,8 +70,82 @@ struct GruLaunch {
     int CT, RT, M, Mp;   // column threads, row threads, rows per tile (RT*SPT), M rounded to 16
     int NTc;             // compute threads rounded up to a warp multiple; block = NTc + kHeadThreads
     int w_smem;          // packed weights resident in shared memory
+    int ring_kc;         // !w_smem: K rows per chunk of the shared-memory weight ring (0: weights read straight from global / L2)
     int smem_bytes;
 };
+
+// Weight ring for stacks whose packed weights do not fit in shared memory (e.g. GRU(100) in float64: 245 KB).  The compute warps
+// stream the h-part (and, above layer 0, the x-part) of a layer's weights through two shared-memory buffers of KC K-rows each with
+// cp.async: every weight crosses L2 -> SM once per CTA and step instead of once per row-thread group, and its latency is hidden
+// behind the FMAs of the previous chunk (ncu of the float64 chain kernel before this: long-scoreboard 4.8 and barrier 3.7 stalls per
+// issue, FP64 pipe 25 % busy).  bar.sync 1 synchronises the NTc compute threads only; the head warps never see it.
+template <typename T> struct WRing {
+    T* buf;      // [2][KC * CT * 6]: per buffer ru rows [KC][CT][4] then c rows [KC][CT][2]
+    int KC, nthr, tid;
+};
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void ring_fetch(const WRing<T>& r, int buf, const T* __restrict__ src_ru, const T* __restrict__ src_c, int rows, int CT) {
+    unsigned char* d_ru = reinterpret_cast<unsigned char*>(r.buf + (size_t)buf * r.KC * CT * 6);
+    unsigned char* d_c = d_ru + (size_t)r.KC * CT * 4 * sizeof(T);
+    const unsigned char* s_ru = reinterpret_cast<const unsigned char*>(src_ru);
+    const unsigned char* s_c = reinterpret_cast<const unsigned char*>(src_c);
+    const int n16 = rows * CT * 4 * (int)sizeof(T) / 16, n8 = rows * CT * 2 * (int)sizeof(T) / 8;
+    for (int i = r.tid; i < n16; i += r.nthr) cp_async16(d_ru + 16 * i, s_ru + 16 * i);
+    for (int i = r.tid; i < n8; i += r.nthr) cp_async8(d_c + 8 * i, s_c + 8 * i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int PENDING> __device__ __forceinline__ void ring_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ void ring_sync(int nthr) { asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); }
+
+// acc += A[K rows of the tile] x W[K][thread's 6 gate columns], the weights of K-row k at ru + (k*CT + ct)*4 and c + (k*CT + ct)*2
+template <typename T>
+__device__ __forceinline__ void preact_rows(const T* __restrict__ a_rows, int M, int k0, int rows, const T* __restrict__ ru, const T* __restrict__ cw,
+                                            int CT, int ct, T (&ar)[2][VT<T>::SPT], T (&au)[2][VT<T>::SPT], T (&acq)[2][VT<T>::SPT]) {
+    constexpr int SPT = VT<T>::SPT;
+#pragma unroll 2
+    for (int k = 0; k < rows; ++k) {
+        T a[SPT], w[4], c[2];
+        ldv<SPT>(a, a_rows + (size_t)(k0 + k) * M);
+        ldv<4>(w, ru + (k * CT + ct) * 4);
+        ldv<2>(c, cw + (k * CT + ct) * 2);
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+            ar[0][s] = fma(a[s], w[0], ar[0][s]);
+            ar[1][s] = fma(a[s], w[1], ar[1][s]);
+            au[0][s] = fma(a[s], w[2], au[0][s]);
+            au[1][s] = fma(a[s], w[3], au[1][s]);
+            acq[0][s] = fma(a[s], c[0], acq[0][s]);
+            acq[1][s] = fma(a[s], c[1], acq[1][s]);
+        }
+    }
+}
+// the same product with the weights streamed through the ring (all r.nthr compute threads call this together)
+template <typename T>
+__device__ __forceinline__ void preact_ring(const WRing<T>& r, const T* __restrict__ a_rows, int M, int K, const T* __restrict__ ru_g,
+                                            const T* __restrict__ c_g, int CT, int ct, T (&ar)[2][VT<T>::SPT], T (&au)[2][VT<T>::SPT],
+                                            T (&acq)[2][VT<T>::SPT]) {
+    const int KC = r.KC, nch = (K + KC - 1) / KC;
+    ring_fetch<T>(r, 0, ru_g, c_g, min(KC, K), CT);
+    for (int i = 0; i < nch; ++i) {
+        const int k0 = i * KC;
+        if (i + 1 < nch) {
+            ring_fetch<T>(r, (i + 1) & 1, ru_g + (size_t)(k0 + KC) * CT * 4, c_g + (size_t)(k0 + KC) * CT * 2, min(KC, K - k0 - KC), CT);
+            ring_wait<1>();
+        } else {
+            ring_wait<0>();
+        }
+        ring_sync(r.nthr);                                   // chunk i has landed for every thread
+        const T* b = r.buf + (size_t)(i & 1) * KC * CT * 6;
+        preact_rows<T>(a_rows, M, k0, min(KC, K - k0), b, b + (size_t)KC * CT * 4, CT, ct, ar, au, acq);
+        ring_sync(r.nthr);                                   // buffer i & 1 may be refilled (chunk i + 2)
+    }
+}
 
 template <typename T>
 __global__ void pack_gru_kernel(GruLayout g, const T* __restrict__ flat, T* __restrict__ pk) {
@@ -134,7 +208,7 @@ __device__ __forceinline__ void gru_preact(const GruLayout& g, int l, const T* _
                                            const T* __restrict__ Ax, const T* __restrict__ Ah,
                                            const uint8_t* __restrict__ sig, int M, int ct, int rt,
                                            T (&ar)[2][VT<T>::SPT], T (&au)[2][VT<T>::SPT], T (&ac)[2][VT<T>::SPT],
-                                           T (&aq)[2][VT<T>::SPT]) {
+                                           T (&aq)[2][VT<T>::SPT], const WRing<T>* ring = nullptr) {
     constexpr int SPT = VT<T>::SPT;
     const int H = g.H, CT = g.CT, d = g.d[l];
     const T* wx_ru = wl;
@@ -168,55 +242,24 @@ __device__ __forceinline__ void gru_preact(const GruLayout& g, int l, const T* _
             ac[0][s] += m0 * c0[0] + m1 * c1[0];
             ac[1][s] += m0 * c0[1] + m1 * c1[1];
         }
+    } else if (ring) {
+        preact_ring<T>(*ring, Ax + row0, M, d, wx_ru, wx_c, CT, ct, ar, au, ac);
     } else {
-        const T* ax = Ax + row0;
-#pragma unroll 2
-        for (int k = 0; k < d; ++k) {
-            T a[SPT], w[4], c[2];
-            ldv<SPT>(a, ax + k * M);
-            ldv<4>(w, wx_ru + (k * CT + ct) * 4);
-            ldv<2>(c, wx_c + (k * CT + ct) * 2);
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) {
-                ar[0][s] = fma(a[s], w[0], ar[0][s]);
-                ar[1][s] = fma(a[s], w[1], ar[1][s]);
-                au[0][s] = fma(a[s], w[2], au[0][s]);
-                au[1][s] = fma(a[s], w[3], au[1][s]);
-                ac[0][s] = fma(a[s], c[0], ac[0][s]);
-                ac[1][s] = fma(a[s], c[1], ac[1][s]);
-            }
-        }
+        preact_rows<T>(Ax + row0, M, 0, d, wx_ru, wx_c, CT, ct, ar, au, ac);
     }
-    {
-        const T* ah = Ah + row0;
-#pragma unroll 2
-        for (int k = 0; k < H; ++k) {
-            T a[SPT], w[4], c[2];
-            ldv<SPT>(a, ah + k * M);
-            ldv<4>(w, wh_ru + (k * CT + ct) * 4);
-            ldv<2>(c, wh_c + (k * CT + ct) * 2);
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) {
-                ar[0][s] = fma(a[s], w[0], ar[0][s]);
-                ar[1][s] = fma(a[s], w[1], ar[1][s]);
-                au[0][s] = fma(a[s], w[2], au[0][s]);
-                au[1][s] = fma(a[s], w[3], au[1][s]);
-                aq[0][s] = fma(a[s], c[0], aq[0][s]);
-                aq[1][s] = fma(a[s], c[1], aq[1][s]);
-            }
-        }
-    }
+    if (ring) preact_ring<T>(*ring, Ah + row0, M, H, wh_ru, wh_c, CT, ct, ar, au, aq);
+    else preact_rows<T>(Ah + row0, M, 0, H, wh_ru, wh_c, CT, ct, ar, au, aq);
 }
 
 template <typename T>
 __device__ __forceinline__ void gru_layer(const GruLayout& g, int l, const T* __restrict__ wl,
                                           const T* __restrict__ Ax, const T* __restrict__ Ah,
                                           const uint8_t* __restrict__ sig, int M, int ct, int rt,
-                                          T (&hn)[2][VT<T>::SPT]) {
+                                          T (&hn)[2][VT<T>::SPT], const WRing<T>* ring = nullptr) {
     constexpr int SPT = VT<T>::SPT;
     const int H = g.H;
     T ar[2][SPT], au[2][SPT], ac[2][SPT], aq[2][SPT];
-    gru_preact<T>(g, l, wl, Ax, Ah, sig, M, ct, rt, ar, au, ac, aq);
+    gru_preact<T>(g, l, wl, Ax, Ah, sig, M, ct, rt, ar, au, ac, aq, ring);
     const int row0 = rt * SPT;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -240,13 +283,15 @@ __device__ __forceinline__ void gru_layer(const GruLayout& g, int l, const T* __
 template <typename T, bool STASH>
 __device__ __forceinline__ void gru_site(const GruLayout& g, const T* __restrict__ w, T* __restrict__ hbuf,
                                          const uint8_t* __restrict__ sigcur, int M, int ct, int rt,
-                                         bool is_compute, T* __restrict__ stash) {
+                                         bool is_compute, T* __restrict__ stash, const WRing<T>* ring = nullptr) {
     constexpr int SPT = VT<T>::SPT;
     const int H = g.H;
     for (int l = 0; l < g.L; ++l) {
         T hn[2][SPT];
         T* hl = hbuf + l * H * M;
-        if (is_compute) gru_layer<T>(g, l, w + g.pk_off[l], l == 0 ? nullptr : hl - H * M, hl, sigcur, M, ct, rt, hn);
+        if (ring) {   // the padding lanes of the last compute warp take part in the ring's copies and barriers (row tile clamped, nothing written)
+            if (ring->tid < ring->nthr) gru_layer<T>(g, l, w + g.pk_off[l], l == 0 ? nullptr : hl - H * M, hl, sigcur, M, ct, min(rt, M / SPT - 1), hn, ring);
+        } else if (is_compute) gru_layer<T>(g, l, w + g.pk_off[l], l == 0 ? nullptr : hl - H * M, hl, sigcur, M, ct, rt, hn);
         __syncthreads();
         if (is_compute) {
 #pragma unroll

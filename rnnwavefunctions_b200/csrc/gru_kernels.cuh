@@ -51,7 +51,7 @@ struct TileSmem {
 
 template <typename T, bool WSMEM>
 __device__ __forceinline__ void tile_setup(const GruLayout& g, const GruLaunch& c, const T* __restrict__ pk,
-                                           unsigned char* smem, const T*& w, T*& hbuf, uint8_t*& sig) {
+                                           unsigned char* smem, const T*& w, T*& hbuf, uint8_t*& sig, WRing<T>* ring = nullptr) {
     size_t off = 0;
     if (WSMEM) {
         T* wsm = reinterpret_cast<T*>(smem);
@@ -64,6 +64,13 @@ __device__ __forceinline__ void tile_setup(const GruLayout& g, const GruLaunch& 
     hbuf = reinterpret_cast<T*>(smem + off);
     off += (size_t)g.L * g.H * c.M * sizeof(T);
     sig = smem + off;
+    if (ring) {   // weight ring behind the spin codes (16-byte aligned); KC == 0: no ring
+        off = (off + 2 * (size_t)c.Mp + 64 + 15) & ~(size_t)15;
+        ring->buf = reinterpret_cast<T*>(smem + off);
+        ring->KC = WSMEM ? 0 : c.ring_kc;
+        ring->nthr = c.NTc;
+        ring->tid = threadIdx.x;
+    }
 }
 
 // =============================================================================================
@@ -83,7 +90,9 @@ gru_forward_kernel(GruLayout g, GruLaunch c, const T* __restrict__ pk, const uin
                    double* __restrict__ ph_oth) {
     extern __shared__ __align__(16) unsigned char smem[];
     const T* w; T* hbuf; uint8_t* sig;
-    tile_setup<T, WSMEM>(g, c, pk, smem, w, hbuf, sig);
+    WRing<T> ring;
+    tile_setup<T, WSMEM>(g, c, pk, smem, w, hbuf, sig, &ring);
+    const WRing<T>* ringp = (!WSMEM && ring.KC > 0) ? &ring : nullptr;
     const int tid = threadIdx.x, M = c.M, Mp = c.Mp, N = g.N, H = g.H, L = g.L;
     const int st = blockIdx.x;
     for (int i = tid; i < L * H * M; i += blockDim.x) hbuf[i] = T(0);
@@ -129,7 +138,7 @@ gru_forward_kernel(GruLayout g, GruLaunch c, const T* __restrict__ pk, const uin
         }
         if (n == N) break;
         T* stash = STASH ? hstore + ((size_t)st * N + n) * L * H * M : nullptr;
-        gru_site<T, STASH>(g, w, hbuf, sig + (n & 1) * Mp, M, ct, rt, is_compute, stash);
+        gru_site<T, STASH>(g, w, hbuf, sig + (n & 1) * Mp, M, ct, rt, is_compute, stash, ringp);
     }
     if (is_head) {
 #pragma unroll
@@ -154,7 +163,9 @@ gru_sample_kernel(GruLayout g, GruLaunch c, const T* __restrict__ pk, uint8_t* _
                   uint64_t sample_offset) {
     extern __shared__ __align__(16) unsigned char smem[];
     const T* w; T* hbuf; uint8_t* sig;
-    tile_setup<T, WSMEM>(g, c, pk, smem, w, hbuf, sig);
+    WRing<T> ring;
+    tile_setup<T, WSMEM>(g, c, pk, smem, w, hbuf, sig, &ring);
+    const WRing<T>* ringp = (!WSMEM && ring.KC > 0) ? &ring : nullptr;
     const int tid = threadIdx.x, M = c.M, Mp = c.Mp, N = g.N, H = g.H, L = g.L;
     const int st = blockIdx.x;
     for (int i = tid; i < L * H * M; i += blockDim.x) hbuf[i] = T(0);
@@ -168,7 +179,7 @@ gru_sample_kernel(GruLayout g, GruLaunch c, const T* __restrict__ pk, uint8_t* _
     const T* wd = w + g.pk_head;
     int nup[2] = {0, 0};
     for (int n = 0; n < N; ++n) {
-        gru_site<T, false>(g, w, hbuf, sig + (n & 1) * Mp, M, ct, rt, is_compute, nullptr);
+        gru_site<T, false>(g, w, hbuf, sig + (n & 1) * Mp, M, ct, rt, is_compute, nullptr, ringp);
         if (is_head) {
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -233,7 +244,9 @@ gru_chain_kernel(GruLayout g, GruLaunch c, ChainPlan plan, const T* __restrict__
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ int s_work;
     const T* w; T* hbuf; uint8_t* sig;
-    tile_setup<T, WSMEM>(g, c, pk, smem, w, hbuf, sig);
+    WRing<T> ring;
+    tile_setup<T, WSMEM>(g, c, pk, smem, w, hbuf, sig, &ring);
+    const WRing<T>* ringp = (!WSMEM && ring.KC > 0) ? &ring : nullptr;
     const int tid = threadIdx.x, M = c.M, Mp = c.Mp, N = g.N, H = g.H, L = g.L;
     const bool is_compute = tid < c.CT * c.RT;
     const int ct = tid % c.CT, rt = tid / c.CT;
@@ -311,7 +324,7 @@ gru_chain_kernel(GruLayout g, GruLaunch c, ChainPlan plan, const T* __restrict__
                 }
             }
             if (n == N) break;
-            gru_site<T, false>(g, w, hbuf, sig + (n & 1) * Mp, M, ct, rt, is_compute, nullptr);
+            gru_site<T, false>(g, w, hbuf, sig + (n & 1) * Mp, M, ct, rt, is_compute, nullptr, ringp);
         }
         if (is_head) {
 #pragma unroll

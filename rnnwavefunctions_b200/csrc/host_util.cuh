@@ -29,6 +29,8 @@ inline double wave_cost(int64_t rows_hint, int ndir, int M, int sms = 148) {
     return (double)((tiles + sms - 1) / sms) * (M + 24);   // + a fixed per-site cost worth ~24 rows (measured: tiny tiles are inefficient)
 }
 
+constexpr int kRingKC = 10;   // K rows per weight-ring chunk (even: keeps the 8- and 16-byte cp.async pieces aligned for float and double)
+
 template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g, int64_t rows_hint = 0, int ndir = 1) {
     constexpr int SPT = VT<T>::SPT;
     GruLaunch best;
@@ -39,8 +41,10 @@ template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g, int
             const int nt = g.CT * RT, M = RT * SPT;
             if (nt > 384 || M > 2 * kHeadThreads) break;
             const int Mp = (M + 15) & ~15;
+            // weights resident (wsm) or streamed through a two-buffer ring of kRingKC K-rows (see WRing in gru_engine.cuh)
+            const size_t ring = wsm ? 0 : 2 * (size_t)kRingKC * g.CT * 6 * sizeof(T) + 16;
             size_t smem = (wsm ? (((size_t)g.PK * sizeof(T) + 15) & ~(size_t)15) : 0) + (size_t)g.L * g.H * M * sizeof(T) +
-                          2 * (size_t)Mp + 64;
+                          2 * (size_t)Mp + 64 + ring;
             if (smem > (size_t)kSmemLimit) break;
             bool take;
             if (rows_hint > 0) {
@@ -54,7 +58,7 @@ template <typename T> inline GruLaunch choose_gru_launch(const GruLayout& g, int
             }
             if (take) {
                 best.CT = g.CT; best.RT = RT; best.M = M; best.Mp = Mp;
-                best.NTc = (nt + 31) & ~31; best.w_smem = wsm; best.smem_bytes = (int)smem;
+                best.NTc = (nt + 31) & ~31; best.w_smem = wsm; best.ring_kc = wsm ? 0 : kRingKC; best.smem_bytes = (int)smem;
             }
         }
         if (best.RT > 0) return best;

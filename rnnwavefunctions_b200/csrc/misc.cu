@@ -106,4 +106,70 @@ int ffma_peak_impl(int iters, double* tflops, cudaStream_t s) {
     return 0;
 }
 
+// FP64 peak probes: the denominators of the roofline of the float64 models (both 2-D apps of the reference compute in float64).
+// mode 0: DFMA, 16 independent accumulator chains per thread; mode 1: mma.sync.m8n8k4.f64 (DMMA), 8 independent accumulator pairs per warp.
+__global__ void __launch_bounds__(256) dfma_probe_kernel(int iters, double a, double b, double* __restrict__ out) {
+    double acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double a, double b, double* __restrict__ out) {
+    double c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c0[i] = (double)(threadIdx.x + i); c1[i] = 0.5 * i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+    if (s == 123.456) out[0] = s;
+}
+
+int fp64_peak_impl(int mode, int iters, double* tflops, cudaStream_t s) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double* out = nullptr;
+    RNNWF_CUDA(cudaMalloc(&out, 8));
+    cudaEvent_t e0, e1;
+    RNNWF_CUDA(cudaEventCreate(&e0));
+    RNNWF_CUDA(cudaEventCreate(&e1));
+    const int grid = sms * 8;
+    auto launch = [&](int n) {
+        if (mode == 0) dfma_probe_kernel<<<grid, 256, 0, s>>>(n, 0.999, 0.001, out);
+        else dmma_probe_kernel<<<grid, 256, 0, s>>>(n, 0.999, 0.001, out);
+    };
+    launch(iters / 8 + 1);
+    RNNWF_CUDA(cudaEventRecord(e0, s));
+    launch(iters);
+    RNNWF_CUDA(cudaEventRecord(e1, s));
+    RNNWF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RNNWF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    // mode 0: 64 FMAs per thread and iteration; mode 1: 16 warp-wide m8n8k4 (256 FMAs each) per warp and iteration
+    const double flops = mode == 0 ? 2.0 * 64.0 * (double)iters * 256.0 * grid : 2.0 * 256.0 * 16.0 * (double)iters * 8.0 * grid;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return 0;
+}
+
 }  // namespace rnnwf

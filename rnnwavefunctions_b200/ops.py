@@ -254,6 +254,13 @@ def ffma_peak(iters=20000):
     return out.value
 
 
+def fp64_peak(mode=0, iters=5000):
+    """Measured FP64 throughput of the current device in TFLOP/s (mode 0: DFMA, 1: DMMA m8n8k4)."""
+    out = C.c_double(0.0)
+    check(_lib.load().rnnwf_fp64_peak(int(mode), int(iters), C.byref(out), _stream()))
+    return out.value
+
+
 @_on_device_of(0)
 def umma_selftest(a, b, passes=3, f16=False, dcol=0):
     """d = a @ b.T on the tcgen05 path (a [128,K], b [N,K] float32 CUDA tensors); f16: FP16 hi/lo operands."""
