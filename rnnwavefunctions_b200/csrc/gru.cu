@@ -264,6 +264,7 @@ static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, ui
 #include "gru_tc.cuh"
 #include "gru_tc16.cuh"
 #include "gru_tc16p.cuh"
+#include "gru_f64mma.cuh"
 namespace rnnwf {
 
 // Chain-kernel selection for the FP32 probability-head pRNN (A/B measurements through RNNWF_CHAIN):
@@ -302,6 +303,7 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
             carve_gru<T>(ws, g, c, tiles, true, g.N, cplx, ns);
             if (std::is_same<T, float>::value && tc_supported(g)) carve_tc(ws, g, make_tc_layout(g), 160);
             if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16_img_bytes(g));
+            if (std::is_same<T, double>::value && f64mma::supported(g)) ws.take<double>(f64mma::make_layout(g).wb_doubles + f64mma::make_layout(g).tab_doubles);
             break;
         case RNNWF_OP_J1J2_ELOC:
             carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns);
@@ -379,6 +381,8 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     unsigned char* img16 = nullptr;
     if (std::is_same<T, float>::value && tc16::supported(g)) img16 = ws.take<unsigned char>(tc16_img_bytes(g));
     const int mode = std::is_same<T, float>::value ? chain_mode(g) : 0;
+    double* wb64 = nullptr;       // float64 one-layer stacks: B fragments + constant table of the DMMA chain kernel (gru_f64mma.cuh)
+    if (std::is_same<T, double>::value && f64mma::supported(g)) wb64 = ws.take<double>(f64mma::make_layout(g).wb_doubles + f64mma::make_layout(g).tab_doubles);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
     prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles_s, ndir);
@@ -401,8 +405,20 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
         }
     } else if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
         if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
-        ChainPlan plan{g.N, g.N, 0, 0, tiles, nullptr, nullptr};
-        if (int e = launch_chain<T, false>(g, c, plan, w, s)) return e;
+        const char* env = getenv("RNNWF_CHAIN");
+        bool dmma_done = false;
+        if constexpr (std::is_same<T, double>::value) {
+            if (wb64 && !(env && strcmp(env, "ffma") == 0)) {   // DMMA chain kernel; RNNWF_CHAIN=ffma keeps the thread-tile engine (A/B)
+                if (int e = f64mma::launch(g, c.M, (int64_t)tiles * c.M, (const double*)params, wb64, wb64 + f64mma::make_layout(g).wb_doubles, w.sigT,
+                                           w.hstore, w.la_sel, w.la_oth, w.delta_re, w.counter, s))
+                    return e;
+                dmma_done = true;
+            }
+        }
+        if (!dmma_done) {
+            ChainPlan plan{g.N, g.N, 0, 0, tiles, nullptr, nullptr};
+            if (int e = launch_chain<T, false>(g, c, plan, w, s)) return e;
+        }
     } else {
         if (int e = launch_forward<T, false, false>(g, c, w, tiles, s)) return e;
     }
