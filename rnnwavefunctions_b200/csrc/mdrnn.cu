@@ -12,6 +12,9 @@
 // sizes) because site p needs the state of the site above it, Nx path steps earlier.  Thread (rt, ct) owns
 // SPT rows x 2 units, as in the GRU engine.  Flat parameter order (TF variable creation order,
 // MDRNNcell.py:21-35 + Dense):  Wh[H,H] | Uh[2,H] | Wv[H,H] | Uv[2,H] | b[H] | Wd[H,2] | bd[2].
+#include <stdlib.h>
+#include <string.h>
+#include <type_traits>
 #include "gru_engine.cuh"
 #include "host_util.cuh"
 #include "api_internal.h"
@@ -545,10 +548,15 @@ __global__ void md_wgrad_scatter_kernel(MdLayout g, const double* __restrict__ p
     }
 }
 
+}  // namespace rnnwf
+#include "mdrnn_f64mma.cuh"
+namespace rnnwf {
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct MdWs {
+    double *mm_wb, *mm_priv;     // float64 DMMA chain kernel (mdrnn_f64mma.cuh): B fragments + table, private state grids
     T *pk, *pkT, *hgrid, *hpriv, *Ggrid, *dzbuf;
     double *lp, *la_sel, *la_oth, *delta, *diag, *partial;
     int* counter;
@@ -575,6 +583,11 @@ static MdWs<T> md_carve(Ws& ws, const MdLayout& g, const MdLaunch& c, int64_t ti
         w.hpriv = ws.take<T>((size_t)sms * c.M * g.N * g.H);
         w.delta = ws.take<double>(rows * g.N);
         w.diag = ws.take<double>((size_t)ns);
+        if (std::is_same<T, double>::value && mdmma::supported(g)) {
+            const mdmma::Layout t = mdmma::make_layout(g);
+            w.mm_wb = ws.take<double>(t.wb_doubles + t.tab_doubles);
+            w.mm_priv = ws.take<double>((size_t)sms * t.priv_doubles);
+        }
     }
     if (op == RNNWF_OP_VMC_GRAD) {
         w.Ggrid = ws.take<T>(rows * g.N * g.H);
@@ -710,7 +723,17 @@ int mdrnn_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* s
     prof_count(); md_pack_kernel<T><<<md_grid_for(g.PK + g.PKT), 256, 0, s>>>(g, (const T*)params, w.pk, w.pkT);
     if (int e = tfim_diag_impl(m, samples, ns, jz, w.diag, s)) return e;
     if (int e = md_launch_forward<T, false>(g, c, w, const_cast<uint8_t*>(samples), ns, tiles, true, 0, 0, s)) return e;
-    if (bx != 0.0) {
+    const char* env = getenv("RNNWF_CHAIN");
+    bool dmma_done = false;
+    if constexpr (std::is_same<T, double>::value) {
+        if (bx != 0.0 && w.mm_wb && !(env && strcmp(env, "ffma") == 0)) {   // DMMA chain kernel; RNNWF_CHAIN=ffma keeps the thread-tile kernel (A/B)
+            if (int e = mdmma::launch(g, c.M, ns, (const double*)params, w.mm_wb, w.mm_wb + mdmma::make_layout(g).wb_doubles, w.mm_priv, samples,
+                                      w.hgrid, w.la_sel, w.la_oth, w.delta, w.counter, sms, s))
+                return e;
+            dmma_done = true;
+        }
+    }
+    if (bx != 0.0 && !dmma_done) {
         RNNWF_CUDA(cudaMemsetAsync(w.counter, 0, sizeof(int), s));
         const int block = std::max(c.NT, (c.M + 31) & ~31);
         const int grid = (int)std::min<int64_t>((int64_t)g.N * tiles, sms);
