@@ -261,8 +261,10 @@ static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, ui
 }
 
 }  // namespace rnnwf
-#include "gru_tc.cuh"
-#include "gru_tc16.cuh"
+#ifdef RNNWF_LEGACY
+#include "gru_tc.cuh"       // generation 1 (3xTF32, site-blocked weight swaps): A/B builds only
+#endif
+#include "gru_tc16.cuh"     // shared 3xFP16 helpers (+ generation 2 under RNNWF_LEGACY)
 #include "gru_tc16p.cuh"
 #include "gru_f64mma.cuh"
 namespace rnnwf {
@@ -273,15 +275,32 @@ namespace rnnwf {
 //   "tc16"          : the same arithmetic with MMA and gate math alternating (gru_tc16.cuh)
 //   "tc32"          : tcgen05 kind::tf32, 3xTF32 operands, site-blocked weight swapping (gru_tc.cuh)
 //   "ffma"          : CUDA-core tile engine (gru_chain_kernel; the path every other shape / dtype takes)
+static bool tc16_any_supported(const GruLayout& g) {
+#ifdef RNNWF_LEGACY
+    if (tc16::supported(g)) return true;
+#endif
+    return tc16p::supported_padded(g);
+}
+// layout the shared E_loc buffers are carved for: the zero-padded 50-unit layout when the tensor-core kernel runs a narrower stack
+template <typename T> static GruLayout carve_layout(const GruLayout& g) {
+    if (std::is_same<T, float>::value && tc16p::supported_padded(g)) return tc16p::padded_layout(g);
+    return g;
+}
 static size_t tc16_img_bytes(const GruLayout& g) {   // one image buffer serves either 3xFP16 kernel generation
-    return std::max<size_t>(tc16::make_layout(g).img_bytes, tc16p::make_layout(g).img_bytes);
+#ifdef RNNWF_LEGACY
+    return std::max<size_t>(tc16::supported(g) ? tc16::make_layout(g).img_bytes : 0, tc16p::make_layout(tc16p::padded_layout(g)).img_bytes);
+#else
+    return tc16p::make_layout(tc16p::padded_layout(g)).img_bytes;
+#endif
 }
 static int chain_mode(const GruLayout& g) {
     const char* e = getenv("RNNWF_CHAIN");
     if (e && strcmp(e, "ffma") == 0) return 0;
+#ifdef RNNWF_LEGACY
     if (e && strcmp(e, "tc32") == 0) return tc_supported(g) ? 1 : 0;
     if (e && strcmp(e, "tc16") == 0) return tc16::supported(g) ? 2 : 0;
-    return tc16p::supported(g) ? 3 : (tc16::supported(g) ? 2 : (tc_supported(g) ? 1 : 0));
+#endif
+    return tc16p::supported_padded(g) ? 3 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -300,15 +319,17 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
         case RNNWF_OP_SAMPLE:
         case RNNWF_OP_LOGPSI: carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns); break;
         case RNNWF_OP_TFIM_ELOC:
-            carve_gru<T>(ws, g, c, tiles, true, g.N, cplx, ns);
+            carve_gru<T>(ws, carve_layout<T>(g), c, tiles, true, g.N, cplx, ns);
+#ifdef RNNWF_LEGACY
             if (std::is_same<T, float>::value && tc_supported(g)) carve_tc(ws, g, make_tc_layout(g), 160);
-            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16_img_bytes(g));
+#endif
+            if (std::is_same<T, float>::value && tc16_any_supported(g)) ws.take<unsigned char>(tc16_img_bytes(g));
             if (std::is_same<T, double>::value && f64mma::supported(g)) ws.take<double>(f64mma::make_layout(g).wb_doubles + f64mma::make_layout(g).tab_doubles);
             break;
         case RNNWF_OP_J1J2_ELOC:
-            carve_gru<T>(ws, g, c, tiles, true, 2 * g.N, cplx, ns);
+            carve_gru<T>(ws, carve_layout<T>(g), c, tiles, true, 2 * g.N, cplx, ns);
             ws.take<float>((size_t)ns * (2 * g.N + 1));
-            if (std::is_same<T, float>::value && tc16::supported(g)) ws.take<unsigned char>(tc16_img_bytes(g));
+            if (std::is_same<T, float>::value && tc16_any_supported(g)) ws.take<unsigned char>(tc16_img_bytes(g));
             break;
         case RNNWF_OP_VMC_GRAD: return gru_grad_workspace_bytes<T>(m, ns, flags);
         default: return 0;
@@ -374,12 +395,14 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     const int parity = (flags & RNNWF_PARITY_SYM) ? 1 : 0;
     const int tiles_s = (int)cdiv(ns, c.M), ndir = parity ? 2 : 1, tiles = tiles_s * ndir;
     Ws ws(wsp, wsb);
-    GruWs<T> w = carve_gru<T>(ws, g, c, tiles, true, g.N, false, ns);
+    GruWs<T> w = carve_gru<T>(ws, carve_layout<T>(g), c, tiles, true, g.N, false, ns);
+#ifdef RNNWF_LEGACY
     TcWs tw{};
     const bool tc = std::is_same<T, float>::value && tc_supported(g);
     if (tc) tw = carve_tc(ws, g, make_tc_layout(g), 160);
+#endif
     unsigned char* img16 = nullptr;
-    if (std::is_same<T, float>::value && tc16::supported(g)) img16 = ws.take<unsigned char>(tc16_img_bytes(g));
+    if (std::is_same<T, float>::value && tc16_any_supported(g)) img16 = ws.take<unsigned char>(tc16_img_bytes(g));
     const int mode = std::is_same<T, float>::value ? chain_mode(g) : 0;
     double* wb64 = nullptr;       // float64 one-layer stacks: B fragments + constant table of the DMMA chain kernel (gru_f64mma.cuh)
     if (std::is_same<T, double>::value && f64mma::supported(g)) wb64 = ws.take<double>(f64mma::make_layout(g).wb_doubles + f64mma::make_layout(g).tab_doubles);
@@ -393,6 +416,7 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
                                            w.counter, bx != 0.0, s))
                 return e;
         }
+#ifdef RNNWF_LEGACY
     } else if (mode == 2) {
         if constexpr (std::is_same<T, float>::value) {
             if (int e = tc16::launch_eloc(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.lp_re, w.delta_re,
@@ -403,6 +427,7 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
         if constexpr (std::is_same<T, float>::value) {
             if (int e = launch_eloc_tc(g, c, w, tw, tiles, (const float*)params, bx != 0.0, s)) return e;
         }
+#endif
     } else if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
         if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
         const char* env = getenv("RNNWF_CHAIN");

@@ -20,6 +20,24 @@
 namespace rnnwf {
 namespace tc16 {
 
+// ---- helpers shared with the pipelined generation (gru_tc16p.cuh); always compiled ------------------------------------------------
+__host__ __device__ __forceinline__ int core_off(int n, int k, int KC) {   // offset in halfs inside a K-major core-matrix image
+    return (n >> 3) * (KC * 64) + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);
+}
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {   // low half = fp16(a), high half = fp16(b)
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    return __half22float2(h);
+}
+
+#ifdef RNNWF_LEGACY   // generation 2 (MMA and gate math alternating): kept for A/B runs (RNNWF_CHAIN=tc16), not in the product build
+
 constexpr int kRows = 128, kRowThreads = 256, kThreads = 288;
 constexpr int kBW = 52;                 // D columns per gate block (multiple of 4: TMEM load alignment)
 constexpr int kNN = 160;                // N of the x-part ([cx|r|u]) and of the h-part ([r|u|ch]) MMAs
@@ -54,9 +72,6 @@ inline bool supported(const GruLayout& g) {
     return make_layout(g).img_bytes + 2048 <= kSmemLimit;
 }
 
-__host__ __device__ __forceinline__ int core_off(int n, int k, int KC) {   // offset in halfs inside a K-major core-matrix image
-    return (n >> 3) * (KC * 64) + (k >> 3) * 64 + (n & 7) * 8 + (k & 7);
-}
 
 // flat TF-order parameters -> shared-memory image.  Weights are pre-scaled so that the gates are 1/(1 + 2^a):
 // r, u rows by -log2(e), candidate rows by 2 log2(e); K column H (times the constant-1 column of the operand regions)
@@ -128,17 +143,6 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
 
 __device__ __forceinline__ void named_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); }
 __device__ __forceinline__ void row_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kRowThreads) : "memory"); }
-__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {   // low half = fp16(a), high half = fp16(b)
-    uint32_t r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
-}
-__device__ __forceinline__ float2 unpack_h2(uint32_t w) {
-    const __half2 h = *reinterpret_cast<const __half2*>(&w);
-    return __half22float2(h);
-}
 
 // unit range of a row thread: part 0 owns units [0, S), part 1 owns [S, H); S multiple of 8
 template <int H, int PART> struct Part {
@@ -581,5 +585,6 @@ static int launch_j1j2(const GruLayout& g, int Mold, int tiles, const float* par
     return launch_chains<true>(a, sms, true, s);
 }
 
+#endif  // RNNWF_LEGACY
 }  // namespace tc16
 }  // namespace rnnwf

@@ -176,14 +176,29 @@ inline bool supported(const GruLayout& g) {
     if (!(g.H == 50 && g.N >= 2 && g.L >= 1 && g.L <= 3)) return false;
     return smem_bytes(make_layout(g)) <= (size_t)kSmemLimit;
 }
+// Narrower stacks (kMinPadH <= H < 50 units) run on the same kernel zero-padded to 50 units: a padded unit has zero weights and
+// biases in and out, so its gates are exactly 1/2, its candidate exactly 0 and its state stays exactly 0 (h' = u (h - c) + c);
+// nothing of it reaches a real unit.  The tensor work is that of 50 units, which beats the CUDA-core engine (7.8x slower per flop
+// at 50 units) down to about (50 / H)^2 = 4.  Only the local-energy paths use this (the gradient's stash keeps the real width).
+constexpr int kMinPadH = 26;
+inline GruLayout padded_layout(const GruLayout& g) {
+    if (g.H >= 50 || g.H < kMinPadH) return g;
+    rnnwf_model m;
+    memset(&m, 0, sizeof(m));
+    m.cell = RNNWF_CELL_GRU; m.head = g.nheads == 2 ? RNNWF_HEAD_COMPLEX : RNNWF_HEAD_PROB; m.dtype = RNNWF_F32;
+    m.num_layers = g.L; m.units = 50; m.n_sites = g.N;
+    return make_gru_layout(m);
+}
+inline bool supported_padded(const GruLayout& g) { return supported(padded_layout(g)); }
 
 // flat TF-order parameters -> shared-memory image.  Weights are pre-scaled so that the gates are 1/(1 + 2^a): r, u rows by
 // -log2(e), candidate rows by 2 log2(e); the constant-1 K column carries the biases bg (h part of r, u), bch (h part of the
 // candidate) and bci (x part of the candidate).  Layer 0: the x images have K = 16 with the two one-hot rows of the input kernels
 // at k = 0, 1 and bci at k = 2.
 // scaled weight of output row n (gate-block layout) of the h image (xpart = 0: [r | u | ch]) or the x image (xpart = 1: [cx | r | u])
-// of layer l for input unit ku in [0, 50), or the bias that rides on the constant-1 column for ku == 50
-__device__ __forceinline__ float packed_weight(const GruLayout& g, const float* __restrict__ flat, int l, int xpart, int n, int ku) {
+// of layer l for input unit ku, or (bias) the bias that rides on the constant-1 column.  g is the REAL layout: rows / columns of
+// units >= g.H (zero padding to 50 units) are zero.
+__device__ __forceinline__ float packed_weight(const GruLayout& g, const float* __restrict__ flat, int l, int xpart, int n, int ku, bool bias) {
     const int H = g.H, d = g.d[l];
     const float kS = -1.4426950408889634f, kC = 2.8853900817779268f;
     const float* Kg = flat + g.flat_off[l];
@@ -194,16 +209,17 @@ __device__ __forceinline__ float packed_weight(const GruLayout& g, const float* 
     const float* bch = bci + H;
     const int blk = n / kBW;
     const int j = blk < 3 ? unit_of_col(n % kBW) : -1;       // output unit of this row (-1: padding)
-    if (j < 0 || ku < 0 || ku > H) return 0.f;
+    if (j < 0 || j >= H) return 0.f;
+    if (!bias && (ku < 0 || ku >= H)) return 0.f;
     const bool cand = xpart ? blk == 0 : blk == 2;
     const int gate = xpart ? blk - 1 : blk;                  // 0: r, 1: u (unused for the candidate block)
     if (!xpart) {
-        if (!cand) return ku < H ? kS * Kg[(d + ku) * 2 * H + gate * H + j] : kS * bg[gate * H + j];
-        return ku < H ? kC * Kch[ku * H + j] : kC * bch[j];
+        if (!cand) return !bias ? kS * Kg[(d + ku) * 2 * H + gate * H + j] : kS * bg[gate * H + j];
+        return !bias ? kC * Kch[ku * H + j] : kC * bch[j];
     }
-    if (ku < H && ku >= d) return 0.f;                       // layer 0: only the two one-hot rows exist
-    if (!cand) return ku < H ? kS * Kg[ku * 2 * H + gate * H + j] : 0.f;
-    return ku < H ? kC * Kci[ku * H + j] : kC * bci[j];
+    if (!bias && ku >= d) return 0.f;                        // layer 0: only the two one-hot rows exist
+    if (!cand) return !bias ? kS * Kg[ku * 2 * H + gate * H + j] : 0.f;
+    return !bias ? kC * Kci[ku * H + j] : kC * bci[j];
 }
 
 __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ flat, unsigned char* __restrict__ img) {
@@ -220,7 +236,7 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         __half* im1 = reinterpret_cast<__half*>(Lb + (xpart ? t.im_bytes + t.im2_bytes : 0));
         if (xpart && l == 0) {                          // one-hot input: K = 16, rows k = 0, 1 of the input kernels, bci at k = 2
             if (k >= 16) continue;
-            const float v = k < 2 ? packed_weight(g, flat, 0, 1, n, k) : (k == 2 ? packed_weight(g, flat, 0, 1, n, H) : 0.f);
+            const float v = k < 2 ? packed_weight(g, flat, 0, 1, n, k, false) : (k == 2 ? packed_weight(g, flat, 0, 1, n, 0, true) : 0.f);
             const __half hi = __float2half_rn(v);
             im1[core_off(n, k, 2)] = hi;
             reinterpret_cast<__half*>(Lb + t.im_bytes + t.im2_bytes + t.im0_bytes)[core_off(n, k, 2)] = __float2half_rn(v - __half2float(hi));
@@ -229,23 +245,23 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         __half* im2 = reinterpret_cast<__half*>(Lb + (xpart ? t.im_bytes + t.im2_bytes : 0) + t.im_bytes);
 #if RNNWF_KPACK
         if (k < kK2 + 2) {                               // units 0..49: hi into B1 at k; lo into B2 (units < 48) or B1 at k + 2 (48, 49)
-            const float v = packed_weight(g, flat, l, xpart, n, k);
+            const float v = packed_weight(g, flat, l, xpart, n, k, false);
             const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
             im1[core_off(n, k, kKC)] = hi;
             if (k < kK2) im2[core_off(n, k, kKC2)] = lo;
             else im1[core_off(n, k + 2, kKC)] = lo;
         } else if (k == 52) {                            // the two halves of the bias against the constant (1, 1)
-            const float v = packed_weight(g, flat, l, xpart, n, H);
+            const float v = packed_weight(g, flat, l, xpart, n, 0, true);
             const __half hi = __float2half_rn(v);
             im1[core_off(n, 52, kKC)] = hi;
             im1[core_off(n, 53, kKC)] = __float2half_rn(v - __half2float(hi));
         } else if (k == 54 || k == 55) {
             im1[core_off(n, k, kKC)] = __float2half_rn(0.f);
         } else if (k >= 56) {                            // c7: copy of c0 (W_hi of units 0..7 against the first lo halves)
-            im1[core_off(n, k, kKC)] = __float2half_rn(packed_weight(g, flat, l, xpart, n, k - 56));
+            im1[core_off(n, k, kKC)] = __float2half_rn(packed_weight(g, flat, l, xpart, n, k - 56, false));
         }
 #else
-        const float v = packed_weight(g, flat, l, xpart, n, k < H ? k : (k == kKOne ? H : -1));
+        const float v = k == kKOne ? packed_weight(g, flat, l, xpart, n, 0, true) : packed_weight(g, flat, l, xpart, n, k < 50 ? k : -1, false);
         const __half hi = __float2half_rn(v);
         im1[core_off(n, k, kKC)] = hi;
         im2[core_off(n, k, kKC)] = __float2half_rn(v - __half2float(hi));
@@ -257,7 +273,7 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         float v = 0.f;
         if (r < 4 * kUP) {                              // part 1's first two slots duplicate units 24, 25 of part 0: zero weights
             const int part = r / (2 * kUP), slot = (r % (2 * kUP)) / 2, o = r & 1;
-            if (!(part == 1 && slot < kUP - kPU)) v = hw[2 * (kPU * part + slot) + o];
+            if (!(part == 1 && slot < kUP - kPU) && kPU * part + slot < H) v = hw[2 * (kPU * part + slot) + o];
         }
         else if (r >= 128 && r < 130) v = hw[2 * H + (r - 128)];
         reinterpret_cast<float*>(img + t.tab_off)[idx] = v;
@@ -1015,23 +1031,25 @@ static Args make_args(const GruLayout& g, int Mold, int tiles, unsigned char* im
 }
 
 // base pass + single-flip chains (FP32 pRNN with 50 units)
-static int launch_eloc(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
+static int launch_eloc(const GruLayout& greal, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
                        double* la_sel, double* la_oth, float* la_self, double* lp, double* delta, int* counter, bool flips, cudaStream_t s) {
     int sms;
+    const GruLayout g = padded_layout(greal);      // hstore, the image and the kernel see 50 units; the pack reads the real widths
     Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, la_self, lp, delta, counter, sms);
-    prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(greal, a.t, params, img);
     return launch_chains<false>(a, sms, flips, s);
 }
 
 // base pass + NN / NNN exchange chains of the complex cRNN (J1-J2); `order` lists the 2N-3 slots by decreasing chain length
-static int launch_j1j2(const GruLayout& g, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
+static int launch_j1j2(const GruLayout& greal, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
                        double* la_sel, double* la_oth, double* ph_sel, double* ph_oth, double* lp_re, double* lp_im, double* delta_re,
                        double* delta_im, const int* order, const double* j1, const double* j2, int* counter, cudaStream_t s) {
     int sms;
+    const GruLayout g = padded_layout(greal);
     Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, nullptr, lp_re, delta_re, counter, sms);
     a.ph_sel = ph_sel; a.ph_oth = ph_oth; a.lp_im = lp_im; a.delta_im = delta_im; a.order = order; a.j1 = j1; a.j2 = j2;
     a.n_kind1 = g.N - 1; a.n_kind2 = g.N - 2; a.nslots = a.n_kind1 + a.n_kind2;
-    prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, img);
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(greal, a.t, params, img);
     return launch_chains<true>(a, sms, true, s);
 }
 

@@ -126,10 +126,10 @@ int gru_j1j2_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     const int tiles = (int)cdiv(ns, c.M);
     const int nslots = 2 * g.N;
     Ws ws(wsp, wsb);
-    GruWs<T> w = carve_gru<T>(ws, g, c, tiles, true, nslots, true, ns);
+    GruWs<T> w = carve_gru<T>(ws, carve_layout<T>(g), c, tiles, true, nslots, true, ns);
     ws.take<float>((size_t)ns * (2 * g.N + 1));                         // (kept for layout compatibility with rnnwf_workspace_bytes)
     unsigned char* img16 = nullptr;
-    if (std::is_same<T, float>::value && tc16::supported(g)) img16 = ws.take<unsigned char>(tc16_img_bytes(g));
+    if (std::is_same<T, float>::value && tc16_any_supported(g)) img16 = ws.take<unsigned char>(tc16_img_bytes(g));
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.pk);
     prof_count(); sig_transpose_kernel<<<grid_for((int64_t)tiles * g.N * c.M), 256, 0, s>>>(samples, w.sigT, ns, g.N, c.M, tiles, 1);
@@ -138,9 +138,14 @@ int gru_j1j2_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
     if (img16 && !(env && strcmp(env, "ffma") == 0)) {   // tcgen05 3xFP16 kernels (gru_tc16p.cuh; RNNWF_CHAIN=tc16: gru_tc16.cuh)
         if constexpr (std::is_same<T, float>::value) {
             prof_count(); chain_order_kernel<<<1, 1, 0, s>>>(plan, w.order);
+#ifdef RNNWF_LEGACY
             const bool gen2 = env && strcmp(env, "tc16") == 0;
-            if (int e = (gen2 ? tc16::launch_j1j2 : tc16p::launch_j1j2)(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth,
-                                          w.lp_re, w.lp_im, w.delta_re, w.delta_im, w.order, j1, j2, w.counter, s))
+            auto launch = gen2 ? tc16::launch_j1j2 : tc16p::launch_j1j2;
+#else
+            auto launch = tc16p::launch_j1j2;
+#endif
+            if (int e = launch(g, c.M, tiles, (const float*)params, img16, w.sigT, w.hstore, w.la_sel, w.la_oth, w.ph_sel, w.ph_oth,
+                               w.lp_re, w.lp_im, w.delta_re, w.delta_im, w.order, j1, j2, w.counter, s))
                 return e;
         }
     } else {

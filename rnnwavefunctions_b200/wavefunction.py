@@ -54,6 +54,11 @@ class _WavefunctionBase:
         npdtype = np.float32 if model.dtype == F32 else np.float64
         self.params = torch.tensor(P.init_flat(shapes, seed, npdtype, mdrnn=mdrnn), device=self.device)
         assert self.params.numel() == ops.param_count(model), (self.params.numel(), ops.param_count(model))
+        if model.cell == CELL_GRU and model.dtype == F32 and model.units > 50 and ops.tfim_chain_mode(model) == 0:
+            import warnings
+            warnings.warn(f"float32 GRU stacks wider than 50 units (here {model.units}) evaluate local energies on the CUDA-core FFMA engine, "
+                          "about 8x slower per flop than the tcgen05 chain kernel that covers 26..50 units and up to 3 layers "
+                          "(rnnwavefunctions_b200/csrc/gru_tc16p.cuh)", RuntimeWarning, stacklevel=3)
         self._draws = 0          # number of sample() calls so far: each call uses a fresh Philox stream offset
         self.sample_offset = 0   # global id of this rank's first sample (set by the data-parallel driver)
         self.graph = None        # the reference exposes .graph (TrainingRNN_1DTFIM.py:107); nothing to expose here

@@ -45,17 +45,17 @@ def test_bx_zero_is_the_diagonal_bit_exact(setup):
 def test_tensor_core_and_cuda_core_chains_agree_at_full_size(setup):
     model, flat, samples = setup
     res = {}
-    for chain in ("ffma", "tc16"):
+    for chain in ("ffma", "tc16p"):
         os.environ["RNNWF_CHAIN"] = chain
         try:
             e, lp = ops.tfim_eloc(model, flat, samples[:256], np.ones(N), 1.0)
             res[chain] = (e.cpu().numpy(), lp.cpu().numpy())
         finally:
             os.environ.pop("RNNWF_CHAIN", None)
-    np.testing.assert_allclose(res["tc16"][0], res["ffma"][0], rtol=1e-5)
-    np.testing.assert_allclose(res["tc16"][1], res["ffma"][1], rtol=1e-5)
-    assert np.all(res["tc16"][0] > -1272.8762953418 - 300)               # local energies scatter around a variational energy
-    assert res["tc16"][0].mean() > -1272.8762953418                      # above the exact ground state (free fermions / DMRG table)
+    np.testing.assert_allclose(res["tc16p"][0], res["ffma"][0], rtol=1e-5)
+    np.testing.assert_allclose(res["tc16p"][1], res["ffma"][1], rtol=1e-5)
+    assert np.all(res["tc16p"][0] > -1272.8762953418 - 300)               # local energies scatter around a variational energy
+    assert res["tc16p"][0].mean() > -1272.8762953418                      # above the exact ground state (free fermions / DMRG table)
 
 
 def test_local_energy_of_three_samples_matches_the_full_recompute_oracle(setup):

@@ -1,4 +1,6 @@
-"""Tensor-core (tcgen05; pipelined 3xFP16 "tc16p", 3xFP16 "tc16", 3xTF32 "tc32") chain kernels vs the CUDA-core chain kernel and the oracle (1e-5 relative gate)."""
+"""Tensor-core (tcgen05, pipelined 3xFP16 "tc16p") chain kernel vs the CUDA-core chain kernel and the oracle (1e-5 relative gate).
+The earlier generations ("tc16": unpipelined 3xFP16, "tc32": 3xTF32) are only compiled with -DRNNWF_LEGACY (A/B builds); their cases
+run when such a library is loaded (RNNWF_LIB) and are skipped for the product build."""
 import os
 
 import numpy as np
@@ -20,6 +22,23 @@ def u8(samples):
     return torch.as_tensor(np.asarray(samples).astype(np.uint8), device=dev())
 
 
+MODE = {"ffma": 0, "tc32": 1, "tc16": 2, "tc16p": 3}
+
+
+def has_chain(chain, model):
+    """Is this chain-kernel generation compiled into the loaded library?"""
+    old = os.environ.get("RNNWF_CHAIN")
+    os.environ["RNNWF_CHAIN"] = chain
+    try:
+        probe = ops.make_model(num_layers=model.num_layers, units=model.units, n_sites=model.n_sites)
+        return ops.tfim_chain_mode(probe) == MODE[chain]
+    finally:
+        if old is None:
+            os.environ.pop("RNNWF_CHAIN", None)
+        else:
+            os.environ["RNNWF_CHAIN"] = old
+
+
 def eloc_with(chain, model, flat, s, Jz, Bx, flags=0):
     old = os.environ.get("RNNWF_CHAIN")
     os.environ["RNNWF_CHAIN"] = chain
@@ -39,6 +58,8 @@ def test_tc_chain_matches_ffma_and_oracle(L, N, ns, parity, chain):
     units = [50] * L
     p = O.randomize_biases(O.init_gru_params(units, seed=L, dtype=np.float32, scale=2.0), seed=L + 1)
     model = ops.make_model(num_layers=L, units=50, n_sites=N)
+    if not has_chain(chain, model):
+        pytest.skip(f"{chain} is a legacy generation (-DRNNWF_LEGACY builds only)")
     flat = torch.tensor(O.flatten(p), device=dev())
     s = O.sample(p, ns, N, seed=3)
     Jz = np.random.default_rng(5).uniform(0.5, 1.5, size=N)
@@ -66,7 +87,9 @@ def test_tc_j1j2_exchange_chains_match_ffma_and_oracle(L, N, ns, marshall, j2):
     if j2:
         J2[2] = 0.0
     out = {}
-    for chain in ("tc16p", "tc16", "ffma"):
+    gens = [c for c in ("tc16p", "tc16") if has_chain(c, model)]
+    assert "tc16p" in gens
+    for chain in gens + ["ffma"]:
         os.environ["RNNWF_CHAIN"] = chain
         try:
             e, la = ops.j1j2_eloc(model, flat, u8(s), J1, J2, Bz, marshall_sign=marshall)
@@ -76,7 +99,7 @@ def test_tc_j1j2_exchange_chains_match_ffma_and_oracle(L, N, ns, marshall, j2):
     ref = O.j1j2_local_energies(J1, J2, Bz, s, lambda c: O.crnn_log_amplitude(p, c), marshall_sign=marshall)
     scale = max(1.0, np.abs(ref).max())
     la_ref = O.crnn_log_amplitude(p, s)
-    for chain in ("tc16p", "tc16"):
+    for chain in gens:
         assert np.abs(out[chain][0] - out["ffma"][0]).max() < 2e-5 * scale
         assert np.abs(out[chain][0] - ref).max() < 3e-5 * scale              # the reference combine is complex64
         np.testing.assert_allclose(out[chain][1].real, la_ref.real, rtol=1e-5, atol=1e-6)
@@ -119,3 +142,43 @@ def test_shortest_chains(L, N):
     ref = O.ising_local_energies(Jz, 0.7, s, lambda c: O.log_probability(p, c))
     np.testing.assert_allclose(e.cpu().numpy(), ref, rtol=1e-5)
     np.testing.assert_allclose(np.exp(lp.cpu().numpy()).sum(), 1.0, rtol=1e-5)      # all 2^N configurations: normalised
+
+
+@pytest.mark.parametrize("H,L,N,ns", [(32, 1, 20, 140), (40, 3, 24, 150), (26, 2, 16, 130)])
+def test_narrower_stacks_run_zero_padded_on_the_tensor_core_kernel(H, L, N, ns):
+    """26 <= num_units < 50 (`num_units` is a kwarg of every run_* driver, 1DTFIM/TrainingRNN_1DTFIM.py:79): the tcgen05 kernel runs the
+    stack zero-padded to 50 units; results must equal the CUDA-core engine's and the oracle's, for the TFIM and the J1-J2 chains."""
+    units = [H] * L
+    p = O.randomize_biases(O.init_gru_params(units, seed=H, dtype=np.float32, scale=2.0), seed=H + 1)
+    model = ops.make_model(num_layers=L, units=H, n_sites=N)
+    assert ops.tfim_chain_mode(model) == 3
+    assert ops.tfim_chain_mode(ops.make_model(num_layers=L, units=20, n_sites=N)) == 0       # too narrow to pay for 50-unit tensor work
+    assert ops.tfim_chain_mode(ops.make_model(num_layers=L, units=64, n_sites=N)) == 0       # wider than the kernel's 50-unit blocks
+    flat = torch.tensor(O.flatten(p), device=dev())
+    s = O.sample(p, ns, N, seed=3)
+    Jz = np.random.default_rng(5).uniform(0.5, 1.5, size=N)
+    e_tc, lp_tc = eloc_with("tc16p", model, flat, u8(s), Jz, 0.9)
+    e_ff, lp_ff = eloc_with("ffma", model, flat, u8(s), Jz, 0.9)
+    ref = O.ising_local_energies(Jz, 0.9, s, lambda c: O.log_probability(p, c))
+    np.testing.assert_allclose(e_tc, ref, rtol=1e-5)
+    np.testing.assert_allclose(e_tc, e_ff, rtol=2e-5)
+    np.testing.assert_allclose(lp_tc, O.log_probability(p, s), rtol=1e-5)
+    np.testing.assert_allclose(ops.logpsi(model, flat, u8(s)).cpu().numpy(), O.log_probability(p, s), rtol=1e-5)
+    # parity-symmetric model and the gradient (CUDA-core path for this width) are unaffected
+    e_par, _ = eloc_with("tc16p", model, flat, u8(s), Jz, 0.9, ops.PARITY_SYM)
+    np.testing.assert_allclose(e_par, O.ising_local_energies(Jz, 0.9, s, lambda c: O.log_probability_parity(p, c)), rtol=1e-5)
+    from oracle import torch_grad as TG
+    w = np.random.default_rng(1).normal(size=ns) / ns
+    got = ops.vmc_grad(model, flat, u8(s), torch.tensor(w, device=dev())).cpu().numpy()
+    want = TG.gru_vmc_grad({k: v.astype(np.float64) for k, v in p.items()}, s, w)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-4
+    if L == 1 and N % 2 == 0:
+        heads = ("wf_dense_ampl", "wf_dense_phase")
+        pc = O.randomize_biases(O.init_gru_params(units, seed=H + 2, dtype=np.float32, heads=heads, scale=1.5), seed=H + 3)
+        mc = ops.make_model(head=ops.HEAD_COMPLEX, num_layers=L, units=H, n_sites=N)
+        fc = torch.tensor(O.flatten(pc), device=dev())
+        sc = O.crnn_sample(pc, 100, N, seed=3)
+        J1, J2, Bz = np.ones(N), 0.2 * np.ones(N), np.zeros(N)
+        e, la = ops.j1j2_eloc(mc, fc, u8(sc), J1, J2, Bz, marshall_sign=True)
+        refc = O.j1j2_local_energies(J1, J2, Bz, sc, lambda c: O.crnn_log_amplitude(pc, c), marshall_sign=True)
+        assert np.abs(e.cpu().numpy() - refc).max() < 3e-5 * max(1.0, np.abs(refc).max())
