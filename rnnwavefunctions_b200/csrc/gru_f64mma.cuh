@@ -28,14 +28,6 @@ struct Layout {
     size_t wb_doubles, tab_doubles;
 };
 
-inline bool supported(const GruLayout& g) {
-    if (g.L != 1 || g.nheads != 1 || g.H < 2 || g.N < 2) return false;
-    const int blocks = (g.H + 7) / 8;
-    if (blocks > kMaxBlocks) return false;
-    if (8 * blocks - g.H < 2 || (g.H % 2) != 0) return false;      // two spare (even-aligned) columns for the head logits
-    return true;
-}
-
 inline Layout make_layout(const GruLayout& g) {
     Layout t;
     t.H = g.H; t.N = g.N;
@@ -51,6 +43,14 @@ inline Layout make_layout(const GruLayout& g) {
 }
 
 inline size_t smem_bytes(const Layout& t) { return (size_t)2 * kRows * t.ldk * sizeof(double) + t.tab_doubles * sizeof(double) + 64; }
+
+inline bool supported(const GruLayout& g) {
+    if (g.L != 1 || g.nheads != 1 || g.H < 2 || g.N < 2) return false;
+    const int blocks = (g.H + 7) / 8;
+    if (blocks > kMaxBlocks) return false;
+    if (8 * blocks - g.H < 2 || (g.H % 2) != 0) return false;      // two spare (even-aligned) columns for the head logits
+    return smem_bytes(make_layout(g)) <= (size_t)kSmemLimit;
+}
 
 // flat TF-order parameters -> B fragments wb[block][gate][kstep][lane] (lane = 4 * column + k: W_gate[4 ks + lane % 4][8 block + lane / 4])
 // and the table of input-dependent constants.  Gate 0: r, 1: u, 2: candidate hidden projection.

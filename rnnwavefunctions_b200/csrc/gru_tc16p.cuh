@@ -58,6 +58,9 @@
 #ifndef RNNWF_EX2POLY
 #define RNNWF_EX2POLY 0   // number of unit pairs (of 13 per row thread) whose candidate 2^a runs on the FMA pipe (ex2_poly2) instead of MUFU
 #endif
+#ifndef RNNWF_PARTS
+#define RNNWF_PARTS 2     // row threads per sample: 2 (26 units each, 8 row warps at 224 registers) or 3 (18 units each, 12 row warps at 152)
+#endif
 #ifndef RNNWF_KPACK
 #define RNNWF_KPACK 1     // 3e: the three split passes packed densely along K (10 MMAs of K = 16 per operand group instead of 12)
 #endif
@@ -113,8 +116,12 @@ __device__ __forceinline__ f2_t ex2_poly2(float a0, float a1) {
                    __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
 }
 
-constexpr int kRows = 128, kRowThreads = 256, kThreads = 384, kMmaWarp = 8;   // warps 9-11 only complete the MMA warp's warpgroup (setmaxnreg)
-constexpr int kUP = 26, kPU = 24;                        // units per row thread; first unit of part 1: part p owns units [24 p, 24 p + 26),
+constexpr int kParts = RNNWF_PARTS;                      // row threads per sample (one warp group of 4 warps per part: TMEM lane quadrants)
+constexpr int kRows = 128, kRowThreads = 128 * kParts, kThreads = kRowThreads + 128, kMmaWarp = 4 * kParts;   // the 3 warps after the MMA warp only complete its warpgroup (setmaxnreg)
+constexpr int kRowRegs = kParts == 2 ? 224 : 152, kMmaRegs = 56;   // kRowThreads * kRowRegs + 128 * kMmaRegs <= 65 536
+constexpr int kUP = kParts == 2 ? 26 : 18, kPU = kParts == 2 ? 24 : 16;   // units per row thread; part p owns units [kPU p, kPU p + kUP),
+constexpr int kG8 = kUP / 8;                             // full groups of 8 units (4 operand columns); kUP = 8 kG8 + 2
+static_assert(kUP == 8 * kG8 + 2 && kPU * (kParts - 1) + kUP == 50 && (kParts == 2 || kParts == 3), "unit partition");
                                                          // units 24 and 25 are computed (identically) by both threads of a sample, so that
                                                          // both halves start at a 4-aligned column and the gate blocks are 52 wide, not 56
 constexpr int kBW = 52;                                  // accumulator columns per gate block: unit j at column j, 2 junk columns
@@ -169,7 +176,7 @@ inline Layout make_layout(const GruLayout& g) {
 
 inline size_t smem_bytes(const Layout& t) {
     // image | head partial sums [2][128] float4 | barriers | tmem slot | work slot (the candidate MMAs over-read <= 1 KB past the images)
-    return (size_t)((t.img_bytes + 15) & ~15) + (size_t)2 * kRows * sizeof(float4) + 128;
+    return (size_t)((t.img_bytes + 15) & ~15) + (size_t)2 * (kParts - 1) * kRows * sizeof(float4) + 128;
 }
 
 inline bool supported(const GruLayout& g) {
@@ -271,9 +278,9 @@ __global__ void pack_kernel(GruLayout g, Layout t, const float* __restrict__ fla
         const int hd = idx / 132, r = idx % 132;        // per head: [part][slot (26)][2] weights of unit 24 part + slot | pad | bd[2] at 128 | pad
         const float* hw = flat + g.flat_head + hd * (2 * H + 2);
         float v = 0.f;
-        if (r < 4 * kUP) {                              // part 1's first two slots duplicate units 24, 25 of part 0: zero weights
+        if (r < 2 * kUP * kParts) {                     // the first two slots of parts >= 1 duplicate the last two units of the part before: zero weights
             const int part = r / (2 * kUP), slot = (r % (2 * kUP)) / 2, o = r & 1;
-            if (!(part == 1 && slot < kUP - kPU) && kPU * part + slot < H) v = hw[2 * (kPU * part + slot) + o];
+            if (!(part >= 1 && slot < kUP - kPU) && kPU * part + slot < H) v = hw[2 * (kPU * part + slot) + o];
         }
         else if (r >= 128 && r < 130) v = hw[2 * H + (r - 128)];
         reinterpret_cast<float*>(img + t.tab_off)[idx] = v;
@@ -314,7 +321,7 @@ template <int NC, bool DUP = false> __device__ __forceinline__ void stage_cols(u
 // the 13th column of a row thread: units 24, 25 (part 0) or 48, 49 (part 1; with dense K packing hi is stored twice)
 __device__ __forceinline__ void stage_tail(uint32_t col, const float* h, int part) {
 #if RNNWF_KPACK
-    if (part) stage_cols<1, true>(col, h);
+    if (part == kParts - 1) stage_cols<1, true>(col, h);
     else
 #endif
         stage_cols<1>(col, h);
@@ -322,8 +329,8 @@ __device__ __forceinline__ void stage_tail(uint32_t col, const float* h, int par
 // the 26 units of a row thread -> columns [12 part, 12 part + 13) of an operand region
 __device__ __forceinline__ void stage_all(uint32_t reg_part_addr, const float* hp, int part) {
 #pragma unroll
-    for (int gq = 0; gq < 3; ++gq) stage_cols<4>(reg_part_addr + 4 * gq, hp + 8 * gq);
-    stage_tail(reg_part_addr + 12, hp + 24, part);
+    for (int gq = 0; gq < kG8; ++gq) stage_cols<4>(reg_part_addr + 4 * gq, hp + 8 * gq);
+    stage_tail(reg_part_addr + 4 * kG8, hp + 8 * kG8, part);
 }
 
 struct Args {
@@ -389,8 +396,9 @@ template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(cons
     umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
     if (!c.live) return;
     float4 pz = c.pz;
-    {
-        const float4 o = c.zsm[c.pbuf * kRows + c.rowi];
+#pragma unroll
+    for (int q = 0; q < kParts - 1; ++q) {
+        const float4 o = c.zsm[(c.pbuf * (kParts - 1) + q) * kRows + c.rowi];
         pz.x += o.x; pz.y += o.y; pz.z += o.z; pz.w += o.w;
     }
     const float* tab = c.tab;
@@ -444,7 +452,11 @@ template <bool BASE, bool LATE = false> __device__ __forceinline__ void finish_h
     c.pn = -1;
     if (!LATE) umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
     if (!c.live) return;
-    const float4 o = c.zsm[c.pbuf * kRows + c.rowi];
+    float4 o = c.zsm[c.pbuf * (kParts - 1) * kRows + c.rowi];
+    if constexpr (kParts == 3) {
+        const float4 o2 = c.zsm[(c.pbuf * (kParts - 1) + 1) * kRows + c.rowi];
+        o.x += o2.x; o.y += o2.y;
+    }
     const float f0 = c.pz.x + o.x + c.tab[128], f1 = c.pz.y + o.y + c.tab[129];
     const float dsel = psg ? f0 - f1 : f1 - f0;                             // z_other - z_selected
     const float ls = dsel > 30.f ? -dsel : -log1pf(expf(dsel));
@@ -544,19 +556,19 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     TCP_T(long long t1 = clock64(); c.w_ru += t1 - t0;)
     float rr[kUP], uu[kUP], dc[kUP], dq[kUP];
 #pragma unroll
-    for (int gq = 0; gq < 3; ++gq) {
+    for (int gq = 0; gq < kG8; ++gq) {
         umma::tmem_ld8p(dpart + kColRU + 8 * gq, rr + 8 * gq);
         umma::tmem_ld8p(dpart + kColRU + kBW + 8 * gq, uu + 8 * gq);
     }
-    umma::tmem_ld2p(dpart + kColRU + 24, rr + 24);
-    umma::tmem_ld2p(dpart + kColRU + kBW + 24, uu + 24);
+    umma::tmem_ld2p(dpart + kColRU + 8 * kG8, rr + 8 * kG8);
+    umma::tmem_ld2p(dpart + kColRU + kBW + 8 * kG8, uu + 8 * kG8);
 #pragma unroll
-    for (int gq = 0; gq < 3; ++gq) {
+    for (int gq = 0; gq < kG8; ++gq) {
         umma::tmem_ld8p(dpart + kColCX + 8 * gq, dc + 8 * gq);
         umma::tmem_ld8p(dpart + kColCH + 8 * gq, dq + 8 * gq);
     }
-    umma::tmem_ld2p(dpart + kColCX + 24, dc + 24);
-    umma::tmem_ld2p(dpart + kColCH + 24, dq + 24);
+    umma::tmem_ld2p(dpart + kColCX + 8 * kG8, dc + 8 * kG8);
+    umma::tmem_ld2p(dpart + kColCH + 8 * kG8, dq + 8 * kG8);
     umma::wait_ld();
     umma::fence_before_sync();
     umma::mbar_arrive(&c.bars[kAccFree]);              // the accumulators may be overwritten by the next step's MMAs
@@ -586,9 +598,9 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     float y0 = 0.f, y1 = 0.f;
     f2_t z01 = f2_make(0.f, 0.f);                      // head partial sums (z0, z1), one packed FMA per unit
 #pragma unroll
-    for (int gq = 0; gq < 4; ++gq) {                   // three column groups of 4 unit pairs and the 13th pair
+    for (int gq = 0; gq <= kG8; ++gq) {                // the column groups of 4 unit pairs and the last pair
 #pragma unroll
-        for (int q = 0; q < (gq < 3 ? 8 : 2); q += 2) {
+        for (int q = 0; q < (gq < kG8 ? 8 : 2); q += 2) {
             const int jl = 8 * gq + q;
 #if RNNWF_FUSED
             ru_pair(rr[jl], uu[jl], rr[jl + 1], uu[jl + 1]);
@@ -641,8 +653,8 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
             }
         }
         // region l takes the new state: it is the h operand of (n + 1, l) and the x operand of (n, l + 1), both visited later
-        if (gq < 3) stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
-        else stage_tail(reg + 12, hp + 24, part);
+        if (gq < kG8) stage_cols<4>(reg + 4 * gq, hp + 8 * gq);
+        else stage_tail(reg + 4 * kG8, hp + 8 * kG8, part);
     }
     if (!BASE && (n == c.s || n == c.t)) spin_n = 1 - spin_n;
     if (part == 1 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
@@ -663,7 +675,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
             c.pph = c.cda;
             c.pbuf = par;
         } else {
-            c.zsm[par * kRows + c.rowi] = make_float4(z0, z1, y0, y1);
+            c.zsm[(par * (kParts - 1) + (part - 1)) * kRows + c.rowi] = make_float4(z0, z1, y0, y1);
         }
     }
     umma::wait_st();
@@ -917,7 +929,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     const Layout& t = a.t;
     const float* tab = reinterpret_cast<const float*>(smem_p16 + t.tab_off);
     float4* zsm = reinterpret_cast<float4*>(smem_p16 + ((t.img_bytes + 15) & ~15));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(zsm + 2 * kRows);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(zsm + 2 * (kParts - 1) * kRows);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
     int* s_work = reinterpret_cast<int*>(tmem_slot + 1);
 
@@ -965,10 +977,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     // the MMA warp hands most of its share to the row warps, which keep three layers' hidden states in registers
     uint32_t gstep;
     if (is_row) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRowRegs));
         gstep = work_loop<BASE, CPLX, true>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
         if (warp == kMmaWarp) gstep = work_loop<BASE, CPLX, false>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
         else gstep = work_loop<BASE, CPLX, false, true>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);   // CTA barriers only
     }

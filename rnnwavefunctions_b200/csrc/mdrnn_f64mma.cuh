@@ -25,7 +25,6 @@ struct Layout {
     size_t wb_doubles, tab_doubles, priv_doubles;   // B fragments, lookup table, private state grid per CTA
 };
 
-inline bool supported(const MdLayout& g) { return g.H >= 2 && (g.H + 7) / 8 <= 13 && g.N >= 2; }
 
 inline Layout make_layout(const MdLayout& g) {
     Layout t;
@@ -42,6 +41,11 @@ inline Layout make_layout(const MdLayout& g) {
 
 inline size_t smem_bytes(const Layout& t) {
     return (size_t)4 * kRows * t.ldk * sizeof(double) + t.tab_doubles * sizeof(double) + (size_t)kRows * t.N + kRows * sizeof(size_t) + 64;
+}
+
+// up to 13 blocks of 8 units (26 compute warps + the head pair), and the four state tiles + the tile's spins must fit in shared memory
+inline bool supported(const MdLayout& g) {
+    return g.H >= 2 && (g.H + 7) / 8 <= 13 && g.N >= 2 && smem_bytes(make_layout(g)) <= (size_t)kSmemLimit;
 }
 
 // flat TF-order parameters (Wh[H,H] | Uh[2,H] | Wv[H,H] | Uv[2,H] | b[H] | Wd[H,2] | bd[2]) -> B fragments

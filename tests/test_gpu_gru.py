@@ -215,3 +215,29 @@ def test_vmc_gradient_f64_exact():
     ref = TG.gru_vmc_grad(p, s, w)
     got = ops.vmc_grad(model, flat, u8(s), torch.tensor(w, device=dev())).cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("H,nx,ny,ns", [(10, 3, 4, 70), (50, 4, 4, 130), (100, 2, 2, 5), (7, 3, 3, 40), (64, 3, 5, 65), (4, 2, 1, 9)])
+def test_f64_one_layer_eloc_dmma_and_thread_tile_kernels_agree_with_oracle(H, nx, ny, ns):
+    """float64 one-layer GRU local energies: the DMMA chain kernel (gru_f64mma.cuh; even widths with two spare columns in the last block
+    of 8 units) and the thread-tile engine (every other width: 7 is odd, 64 fills its blocks) against the oracle's full recompute,
+    incl. ragged sample counts (partly filled 64-row tiles), the shortest lattices and a weight ring that does not divide the width."""
+    import os
+    N = nx * ny
+    p, model, flat = gru_setup([H], N, dtype=np.float64, nx=nx, ny=ny, scale=2.0 if H < 60 else 1.0)
+    s = O.sample(p, ns, N, seed=3)
+    Jz = np.random.default_rng(5).uniform(0.5, 1.5, size=(nx, ny))
+    ref = O.ising2d_local_energies(Jz, 1.7, nx, ny, s, lambda c: O.log_probability(p, c), flat=True)
+    eloc, logp = ops.tfim_eloc(model, flat, u8(s), Jz, 1.7)
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=1e-10)
+    np.testing.assert_allclose(logp.cpu().numpy(), O.log_probability(p, s), rtol=1e-11)
+    os.environ["RNNWF_CHAIN"] = "ffma"
+    try:
+        e2, _ = ops.tfim_eloc(model, flat, u8(s), Jz, 1.7)
+    finally:
+        os.environ.pop("RNNWF_CHAIN", None)
+    np.testing.assert_allclose(e2.cpu().numpy(), ref, rtol=1e-10)
+    # parity symmetry through the same kernels (rows of both directions)
+    refp = O.ising2d_local_energies(Jz, 1.7, nx, ny, s, lambda c: O.log_probability_parity(p, c), flat=True)
+    ep, _ = ops.tfim_eloc(model, flat, u8(s), Jz, 1.7, flags=ops.PARITY_SYM)
+    np.testing.assert_allclose(ep.cpu().numpy(), refp, rtol=1e-10)

@@ -102,3 +102,24 @@ def test_vmc_gradient(H, Nx, Ny, ns):
     ref = TG.mdrnn_vmc_grad(p, s, w)
     got = ops.vmc_grad(model, flat, u8(s), torch.tensor(w, device=dev())).cpu().numpy()
     np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-11)
+
+
+@pytest.mark.parametrize("H,Nx,Ny,ns", [(10, 3, 5, 70), (36, 4, 4, 130), (100, 2, 3, 5), (7, 1, 6, 33), (9, 6, 1, 20), (104, 3, 3, 12), (120, 3, 2, 9)])
+def test_eloc_dmma_and_thread_tile_kernels_agree_with_oracle(H, Nx, Ny, ns):
+    """2-D RNN local energies on the DMMA chain kernel (mdrnn_f64mma.cuh: up to 13 blocks of 8 units, odd widths and K padding
+    included) and on the thread-tile kernel (RNNWF_CHAIN=ffma; widths beyond 104) against the oracle, with ragged sample counts,
+    single-row / single-column lattices (no up / no left neighbour anywhere) and row turn-arounds."""
+    import os
+    p, model, flat = md_setup(H, Nx, Ny, scale=1.5 if H < 50 else 0.5)
+    s = O.mdrnn_sample(p, ns, Nx, Ny, seed=4)
+    Jz = np.random.default_rng(5).uniform(0.5, 1.5, size=(Nx, Ny))
+    ref = O.ising2d_local_energies(Jz, 2.0, Nx, Ny, s, lambda c: O.mdrnn_log_probability(p, c), flat=False)
+    eloc, logp = ops.tfim_eloc(model, flat, u8(s), Jz, 2.0)
+    np.testing.assert_allclose(eloc.cpu().numpy(), ref, rtol=1e-10)
+    np.testing.assert_allclose(logp.cpu().numpy(), O.mdrnn_log_probability(p, s), rtol=1e-11)
+    os.environ["RNNWF_CHAIN"] = "ffma"
+    try:
+        e2, _ = ops.tfim_eloc(model, flat, u8(s), Jz, 2.0)
+    finally:
+        os.environ.pop("RNNWF_CHAIN", None)
+    np.testing.assert_allclose(e2.cpu().numpy(), ref, rtol=1e-10)
