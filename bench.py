@@ -465,12 +465,14 @@ def run_b200_arm(args):
     if not args.no_e2e:
         k_e2e = max(1, min(args.steps, 2))
         h2d = d2h = 0
+        from rnnwavefunctions_b200.wavefunction import Session
+        sess = Session()
         kind = c["kind"]
 
         def host_step():
             nonlocal h2d, d2h
-            samples = wf.sample(ns, 2).cpu().numpy()                         # sess.run(samples_) -> NumPy (int64)
-            d2h += samples.nbytes
+            samples = sess.run(wf.sample(ns, 2))                             # sess.run(samples_) -> NumPy (int64), as TrainingRNN_1DTFIM.py:203
+            d2h += ns * N                                                     # one byte per site crosses PCIe; widened to int64 on the host
             if kind == "tfim1d":
                 eloc = TR.Ising_local_energies(np.ones(N), c["bx"], samples, None, wf, None, None, None)     # host in, host out
             elif kind in ("tfim2d_flat", "tfim2d_mdrnn"):
@@ -501,7 +503,7 @@ def run_b200_arm(args):
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         e2e = {"value": world * ns * k_e2e / (float(t2.item()) * 1e-3), "unit": "samples/s", "steps": k_e2e,
                "h2d_bytes_per_step": h2d // k_e2e, "d2h_bytes_per_step": d2h // k_e2e,
-               "api": "RNNwavefunction.sample -> NumPy; local energies from host samples -> NumPy; optimiser step fed from host arrays"}
+               "api": "sess.run(RNNwavefunction.sample(...)) -> NumPy int64; local energies from host samples -> NumPy; optimiser step fed from host arrays"}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------------------------
     cpu = None

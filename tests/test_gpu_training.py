@@ -174,3 +174,22 @@ def test_reference_layout_shims_import():
             assert hasattr(importlib.import_module(wfmod), "RNNwavefunction")
         finally:
             sys.path.pop(0)
+
+
+def test_session_run_materialises_samples_and_tensors_like_sess_run():
+    """`samples = sess.run(samples_)` (1DTFIM/TrainingRNN_1DTFIM.py:203): int64 host array equal to the device tensor, through the
+    pinned one-byte-per-site path; other tensors and nested fetches come back as NumPy arrays too."""
+    from rnnwavefunctions_b200.wavefunction import RNNwavefunction1D, RNNwavefunction2D, Session
+    sess = Session()
+    wf = RNNwavefunction1D(12, units=[10], seed=3)
+    t = wf.sample(300, 2)
+    h = sess.run(t)
+    assert h.dtype == np.int64 and h.shape == (300, 12) and np.array_equal(h, t.cpu().numpy())
+    h2 = sess.run(wf.sample(200, 2))                      # the staging buffer is reused: earlier results must not change
+    assert np.array_equal(h, t.cpu().numpy()) and h2.shape == (200, 12)
+    lp = wf.log_probability(h)
+    a, (b,) = sess.run([lp, (lp * 2,)])
+    assert np.array_equal(a, lp.cpu().numpy()) and np.array_equal(b, 2 * a)
+    wf2 = RNNwavefunction2D(3, 4, units=[6], seed=3)
+    t2 = wf2.sample(50, 2)
+    assert np.array_equal(sess.run(t2), t2.cpu().numpy()) and sess.run(t2).shape == (50, 3, 4)
