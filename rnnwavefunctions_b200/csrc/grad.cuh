@@ -18,6 +18,7 @@ namespace rnnwf {
 
 struct BwdLaunch {
     int CT, RT, M, Mp, NT, w_smem, smem_bytes;
+    int tc;   // backward recurrence on the tensor cores (gru_tc16b.cuh): M is then that kernel's tile, not RT * SPT
 };
 
 struct GruLayoutT {   // transposed packed weights for the backward GEMMs
@@ -773,12 +774,14 @@ template <typename T> struct GradWs {
     T *dxbuf, *Gbuf, *dzbuf;
     double* partial;
     unsigned char* img16;   // weight image of the tensor-core base pass (FP32 probability-head models it supports)
+    float* gstore;          // backward factors [tile][site][layer][5][unit][M] written by that pass for the tensor-core recurrence
+    unsigned char* img16b;  // transposed-weight images of the tensor-core backward recurrence (gru_tc16b.cuh)
     int ksplit, Rp, Cp;
 };
 
 template <typename T>
 static GradWs<T> carve_grad(Ws& ws, const GruLayout& g, const GruLayoutT& gt, const GruLaunch& cf, int64_t tiles, bool cplx,
-                            int64_t ns) {
+                            int64_t ns, bool tc_bwd) {
     GradWs<T> w;
     w.f = carve_gru<T>(ws, g, cf, tiles, true, 0, cplx, ns);
     const size_t rows = (size_t)tiles * cf.M;
@@ -795,6 +798,12 @@ static GradWs<T> carve_grad(Ws& ws, const GruLayout& g, const GruLayoutT& gt, co
     w.partial = ws.take<double>((size_t)w.ksplit * w.Rp * w.Cp);
     w.img16 = nullptr;
     if (std::is_same<T, float>::value && !cplx && tc16p::supported(g)) w.img16 = ws.take<unsigned char>(tc16p::make_layout(g).img_bytes);
+    w.gstore = nullptr;
+    w.img16b = nullptr;
+    if (tc_bwd) {
+        w.gstore = ws.take<float>(rows * g.N * g.L * tc16b::kFactors * g.H);
+        w.img16b = ws.take<unsigned char>(tc16b::make_layout(1, cf.M).img_bytes);
+    }
     return w;
 }
 
@@ -808,15 +817,28 @@ template <typename T> static GruLaunch fwd_launch_for(const GruLayout& g, const 
     return c;
 }
 
+// launch geometry of the gradient: the CUDA-core tile, or -- FP32 probability-head stacks the tensor-core kernels cover -- tiles that
+// fill the SMs in whole waves for the tensor-core backward recurrence (RNNWF_BWD_FFMA=1 keeps the CUDA-core recurrence: A/B runs)
+template <typename T> static BwdLaunch grad_launch(const GruLayout& g, int64_t ns, int ndir, bool cplx) {
+    BwdLaunch b = choose_bwd_launch<T>(g, ns, ndir);
+    b.tc = 0;
+    if (b.RT > 0 && std::is_same<T, float>::value && !cplx && tc16b::supported(g) && chain_mode(g) == 3 && !getenv("RNNWF_BWD_FFMA")) {
+        b.M = tc16b::choose_rows(ns * ndir);
+        b.Mp = (b.M + 15) & ~15;
+        b.tc = 1;
+    }
+    return b;
+}
+
 template <typename T> size_t gru_grad_workspace_bytes(const rnnwf_model& m, int64_t ns, int flags) {
     const GruLayout g = make_gru_layout(m);
     const GruLayoutT gt = make_gru_layout_T(g);
     const int ndir = (flags & RNNWF_PARITY_SYM) ? 2 : 1;
-    const BwdLaunch b = choose_bwd_launch<T>(g, ns, ndir);
+    const BwdLaunch b = grad_launch<T>(g, ns, ndir, m.head == RNNWF_HEAD_COMPLEX);
     if (b.RT == 0) return 0;
     const GruLaunch cf = fwd_launch_for<T>(g, b);
     Ws ws(nullptr, 0);
-    carve_grad<T>(ws, g, gt, cf, ndir * cdiv(ns, b.M), m.head == RNNWF_HEAD_COMPLEX, ns);
+    carve_grad<T>(ws, g, gt, cf, ndir * cdiv(ns, b.M), m.head == RNNWF_HEAD_COMPLEX, ns, b.tc != 0);
     return ws.used + 256;
 }
 template size_t gru_grad_workspace_bytes<float>(const rnnwf_model&, int64_t, int);
@@ -895,7 +917,7 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
                    double* grad, void* wsp, size_t wsb, cudaStream_t s) {
     const GruLayout g = make_gru_layout(m);
     const GruLayoutT gt = make_gru_layout_T(g);
-    const BwdLaunch b = choose_bwd_launch<T>(g, ns, (flags & RNNWF_PARITY_SYM) ? 2 : 1);
+    const BwdLaunch b = grad_launch<T>(g, ns, (flags & RNNWF_PARITY_SYM) ? 2 : 1, m.head == RNNWF_HEAD_COMPLEX);
     RNNWF_CHECK(b.RT > 0, -3, "no backward launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
     const GruLaunch cf = fwd_launch_for<T>(g, b);
     const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
@@ -904,7 +926,7 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
     const int tiles_s = (int)cdiv(ns, b.M), ndir = parity ? 2 : 1, tiles = tiles_s * ndir;
     const int64_t rows_total = (int64_t)tiles * b.M;
     Ws ws(wsp, wsb);
-    GradWs<T> w = carve_grad<T>(ws, g, gt, cf, tiles, cplx, ns);
+    GradWs<T> w = carve_grad<T>(ws, g, gt, cf, tiles, cplx, ns, b.tc != 0);
     RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
     prof_count(); pack_gru_kernel<T><<<grid_for(g.PK), 256, 0, s>>>(g, (const T*)params, w.f.pk);
     prof_count(); pack_gru_T_kernel<T><<<grid_for(gt.total), 256, 0, s>>>(g, gt, (const T*)params, w.pkT);
@@ -912,11 +934,12 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
     // teacher-forced pass with stash: the tensor-core base pass where it applies (same stash layout, 128-row work items), else the
     // FFMA tile engine
     int e = 0;
-    bool stashed = false;
+    bool stashed = false, tc_bwd = false;
     if constexpr (std::is_same<T, float>::value) {
         if (w.img16 && chain_mode(g) == 3) {
+            tc_bwd = b.tc != 0 && w.gstore != nullptr;
             e = tc16p::launch_eloc(g, b.M, tiles, (const float*)params, w.img16, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.la_self,
-                                   w.f.lp_re, nullptr, w.f.counter, false, s);
+                                   w.f.lp_re, nullptr, w.f.counter, false, s, tc_bwd ? w.gstore : nullptr);
             stashed = true;
         }
     }
@@ -924,7 +947,12 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
     if (e) return e;
     prof_count(); row_weight_kernel<<<grid_for(rows_total), 256, 0, s>>>(weights, w.f.lp_re, ns, b.M, tiles_s, parity, cplx, w.roww);
     for (int l = g.L - 1; l >= 0; --l) {
-        e = cplx ? launch_bwd_layer<T, true>(g, gt, b, l, w, tiles, rows_total, s) : launch_bwd_layer<T, false>(g, gt, b, l, w, tiles, rows_total, s);
+        if (tc_bwd) {
+            if constexpr (std::is_same<T, float>::value)
+                e = tc16b::launch(g, l, b.M, tiles, (const float*)params, w.img16b, w.gstore, w.f.sigT, w.f.la_oth, w.roww, w.dxbuf, w.Gbuf, w.dzbuf, s);
+        } else {
+            e = cplx ? launch_bwd_layer<T, true>(g, gt, b, l, w, tiles, rows_total, s) : launch_bwd_layer<T, false>(g, gt, b, l, w, tiles, rows_total, s);
+        }
         if (e) return e;
         if (l == g.L - 1)
             if ((e = launch_wgrad<T>(g, w, b.M, (int64_t)tiles * g.N, l, true, grad, s))) return e;

@@ -267,6 +267,7 @@ static int launch_sample(const GruLayout& g, const GruLaunch& c, const T* pk, ui
 #include "gru_tc16.cuh"     // shared 3xFP16 helpers (+ generation 2 under RNNWF_LEGACY)
 #include "gru_tc16p.cuh"
 #include "gru_f64mma.cuh"
+#include "gru_tc16b.cuh"
 namespace rnnwf {
 
 // Chain-kernel selection for the FP32 probability-head pRNN (A/B measurements through RNNWF_CHAIN):

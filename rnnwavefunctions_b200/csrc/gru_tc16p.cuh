@@ -342,6 +342,7 @@ struct Args {
     const uint8_t* sigT;
     float* hstore;            // BASE: written (every layer, every site); FLIP: restart states
     double *la_sel, *la_oth;  // BASE: written; FLIP: read (at the modified site only)
+    float* gstore;            // BASE, optional: backward factors [tile][site][layer][5][unit][M] for the tensor-core BPTT (gru_tc16b.cuh)
     float* la_self;           // FP32 copy of la_sel (the values are FP32 numbers): what the flip chains subtract site by site
     double* lp;               // BASE: sum_n la_sel
     double* delta;            // FLIP: [tile][slot][M]
@@ -473,6 +474,21 @@ template <bool BASE, bool LATE = false> __device__ __forceinline__ void finish_h
     const float y = term - c.compf, t = c.accf + y;
     c.compf = (t - c.accf) - y;
     c.accf = t;
+}
+
+// What the backward recurrence of one unit needs from the forward pass, as five factors of d h (gru_tc16b.cuh):
+//   u: d h_{n-1} += d h * u;   alpha = (1-u)(1-c^2): d a_c = d h * alpha;   beta = (h_prev - c) u (1-u): d a_u = d h * beta;
+//   gamma = alpha * aq * r (1-r): d a_r = d h * gamma;   rho = alpha * r: d aq = d h * rho         (aq = h Kch + bch = dq / (2 log2 e))
+// The stash keeps them as [factor][unit][row] (a warp's 32 rows are one 128-byte store; [factor][row][unit] with 8-byte stores per
+// unit pair was measured 2.4x slower: 32 sectors per store instruction instead of 4-5).
+__device__ __forceinline__ void store_bwd_factors(float* gs, size_t AS, float u, float r, float c, float dq, float hprev) {
+    const float aq = dq * 0.34657359027997264f;            // 1 / (2 log2 e): the candidate rows of the images are pre-scaled
+    const float al = (1.0f - u) * (1.0f - c * c);
+    gs[0] = u;
+    gs[AS] = al;
+    gs[2 * AS] = (hprev - c) * u * (1.0f - u);
+    gs[3 * AS] = al * aq * r * (1.0f - r);
+    gs[4 * AS] = al * r;
 }
 
 // reset / update gates 1/(1 + 2^a) of two units, in place.  RNNWF_GATES selects how many reciprocals are shared (MUFU pipe against
@@ -634,6 +650,20 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
 #endif
             f2_split(f2_fma(f2_make(uu[jl], uu[jl + 1]), f2_sub(f2_make(hp[jl], hp[jl + 1]), cc), cc), h0, h1);
 #endif
+            if constexpr (BASE) {
+                if (a.gstore != nullptr && c.live) {   // gradient's stash pass: the factors of the backward recurrence (hp still holds h_prev)
+                    float cs0, cs1;
+#if RNNWF_CAND < 2
+                    cs0 = c0; cs1 = c1;
+#else
+                    f2_split(cc, cs0, cs1);
+#endif
+                    const size_t AS = (size_t)H * Mold;
+                    float* gs = a.gstore + ((((c.rowbase + n) * L + l) * 5) * (size_t)H + kPU * part + jl) * Mold + c.m;
+                    store_bwd_factors(gs, AS, uu[jl], rr[jl], cs0, dq[jl], hp[jl]);
+                    store_bwd_factors(gs + Mold, AS, uu[jl + 1], rr[jl + 1], cs1, dq[jl + 1], hp[jl + 1]);
+                }
+            }
             hp[jl] = h0;
             hp[jl + 1] = h1;
             if (top) {
@@ -1044,10 +1074,12 @@ static Args make_args(const GruLayout& g, int Mold, int tiles, unsigned char* im
 
 // base pass + single-flip chains (FP32 pRNN with 50 units)
 static int launch_eloc(const GruLayout& greal, int Mold, int tiles, const float* params, unsigned char* img, const uint8_t* sigT, float* hstore,
-                       double* la_sel, double* la_oth, float* la_self, double* lp, double* delta, int* counter, bool flips, cudaStream_t s) {
+                       double* la_sel, double* la_oth, float* la_self, double* lp, double* delta, int* counter, bool flips, cudaStream_t s,
+                       float* gstore = nullptr) {
     int sms;
     const GruLayout g = padded_layout(greal);      // hstore, the image and the kernel see 50 units; the pack reads the real widths
     Args a = make_args(g, Mold, tiles, img, sigT, hstore, la_sel, la_oth, la_self, lp, delta, counter, sms);
+    a.gstore = gstore;
     prof_count(); pack_kernel<<<148, 256, 0, s>>>(greal, a.t, params, img);
     return launch_chains<false>(a, sms, flips, s);
 }
