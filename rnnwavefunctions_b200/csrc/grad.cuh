@@ -774,7 +774,7 @@ template <typename T> struct GradWs {
     T *dxbuf, *Gbuf, *dzbuf;
     double* partial;
     unsigned char* img16;   // weight image of the tensor-core base pass (FP32 probability-head models it supports)
-    float* gstore;          // backward factors [tile][site][layer][5][unit][M] written by that pass for the tensor-core recurrence
+    float* gstore;          // backward factors [tile][site][layer]{[unit][M][4], [unit][M]} written by that pass for the tensor-core recurrence
     unsigned char* img16b;  // transposed-weight images of the tensor-core backward recurrence (gru_tc16b.cuh)
     int ksplit, Rp, Cp;
 };

@@ -15,7 +15,7 @@
 //
 // One CTA per tile of M <= 68 rows (the gradient's tiles are sized so that they fill the SMs in whole waves: the walk over the N
 // sites is sequential, tiles are the only parallelism), 8 row warps (two threads per row, 26 units each, as in gru_tc16p.cuh), the
-// MMA warp and a producer thread.  The stash keeps a (tile, site, layer) block of factors contiguous ([factor][unit][row], 68 KB at
+// MMA warp and a producer thread.  The stash keeps a (tile, site, layer) block of factors contiguous ([unit][row][4 factors] + [unit][row], 68 KB at
 // M = 68): the producer brings the block of the next site in with one bulk async copy (TMA) into a two-deep shared-memory ring, two
 // sites ahead of its use (first version: 130 four-byte cp.async per thread and site -- 2 300 instructions per thread and site and
 // the HBM latency exposed every site: 8.3 us per site).
@@ -99,7 +99,7 @@ struct Args {
     int l, M, top;
     const unsigned char* img;
     const float* flat;            // head weights (top layer)
-    const float* gstore;          // [tile][site][layer][5][unit][M]
+    const float* gstore;          // [tile][site][layer]{[unit][M][u, alpha, beta, gamma], [unit][M] rho}
     const uint8_t* sigT;          // [tile][site][M]
     const double* la_oth;         // [tile][site][M]
     const double* roww;           // [tile][M]
@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_kernel(const __grid_constant_
             const int it = N - 1 - n, buf = it & 1;
             umma::mbar_wait(&bars[kBFac0 + buf], (uint32_t)(it >> 1) & 1);                    // the factors of site n have landed
             {   // every lane runs this (tcgen05.st is warp-collective); lanes beyond the tile repeat row 0 and store nothing
-                const float* f0 = reinterpret_cast<const float*>(smem_b16 + t.fac_off + buf * fac_stride) + (size_t)(kPU * part) * M + m;
+                const float* fb0 = reinterpret_cast<const float*>(smem_b16 + t.fac_off + buf * fac_stride);
+                const float* f4 = fb0 + 4 * ((size_t)(kPU * part) * M + m);                   // [unit][row][u, alpha, beta, gamma]
+                const float* frho = fb0 + 4 * (size_t)H * M + (size_t)(kPU * part) * M + m;  // [unit][row] rho
                 float* gout = a.Gbuf + ((rb + n) * 4 * (size_t)H + kPU * part) * M + m;
                 const size_t AS = (size_t)H * M;
 #pragma unroll
@@ -246,13 +248,13 @@ __global__ void __launch_bounds__(kThreads, 1) bwd_kernel(const __grid_constant_
                     float v[8];                                             // (d a_r, d a_u, d a_c, d aq) of units jl, jl + 1
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        const float* f = f0 + (size_t)(jl + e) * M;
+                        const float4 f = *reinterpret_cast<const float4*>(f4 + 4 * (size_t)(jl + e) * M);
                         const float d = dh[jl + e];
-                        cdir[jl + e] = d * f[0];
-                        v[4 + e] = d * f[AS];
-                        v[2 + e] = d * f[2 * AS];
-                        v[0 + e] = d * f[3 * AS];
-                        v[6 + e] = d * f[4 * AS];
+                        cdir[jl + e] = d * f.x;
+                        v[4 + e] = d * f.y;
+                        v[2 + e] = d * f.z;
+                        v[0 + e] = d * f.w;
+                        v[6 + e] = d * frho[(size_t)(jl + e) * M];
                         if (live) {
                             float* go = gout + (size_t)(jl + e) * M;
                             go[0] = wrow * v[0 + e];

@@ -143,7 +143,13 @@ constexpr int kLoCol = 28, kOneCol = 26, kK2 = 48, kKC2 = 6;
 constexpr int kLoCol = 32;
 #endif
 constexpr int kKOne = 50;                                // K index of the constant-1 (bias) column (unpacked layout)
-enum { kFull = 0, kAccFree = 1, kCDone = 2, kWImg = 3, kNumBars = 4 };
+enum { kFull = 0, kAccFree = 1, kCDone = 2, kWImg = 3, kZDone = 4, kNumBars = 5 };
+// kCDone counts ARRIVALS, not steps: in a three-layer stack a fast warp may finish step g + 1 (whose MMAs wait for kAccFree only)
+// before a slow warp has finished step g, so its phase g can complete with the slow warp's arrival still missing.  That is harmless
+// for its one waiter in the site loop -- the MMA warp waits for the phase of the step right before the one it issues, which no thread
+// can over-arrive on -- but a row thread must not read another warp's shared-memory partials behind it: the head partial sums have
+// their own barrier kZDone (arrivals: the part >= 1 threads of a top-layer step, after their zsm store; top-layer steps are at least
+// two steps apart and the skew between warps is at most one step, so its phases are exact).
 
 __host__ __device__ __forceinline__ int unit_of_col(int c) { return c < 50 ? c : -1; }   // gate-block column -> unit
 __host__ __device__ __forceinline__ int unit_of_k(int k) { return k < 50 ? k : -1; }     // operand K index -> unit
@@ -342,7 +348,7 @@ struct Args {
     const uint8_t* sigT;
     float* hstore;            // BASE: written (every layer, every site); FLIP: restart states
     double *la_sel, *la_oth;  // BASE: written; FLIP: read (at the modified site only)
-    float* gstore;            // BASE, optional: backward factors [tile][site][layer][5][unit][M] for the tensor-core BPTT (gru_tc16b.cuh)
+    float* gstore;            // BASE, optional: backward factors [tile][site][layer]{[unit][M][4], [unit][M]} for the tensor-core BPTT (gru_tc16b.cuh)
     float* la_self;           // FP32 copy of la_sel (the values are FP32 numbers): what the flip chains subtract site by site
     double* lp;               // BASE: sum_n la_sel
     double* delta;            // FLIP: [tile][slot][M]
@@ -364,7 +370,7 @@ struct Ctx {
     bool live;
     size_t rowbase;
     int s, t;                 // modified sites (s = -1: none)
-    uint32_t g, cda;          // steps done by this CTA so far (phase index of full_ru / full_c / ru_free); next c_done phase index
+    uint32_t g, cda, zc;      // steps done by this CTA so far (phase index of full_ru / full_c / ru_free); next c_done phase index; top-layer steps so far (z_done phase index)
     float4 pz;                // pending head (part 0): partial sums, selected outcome, site, c_done phase and zsm buffer of that step
     int psg, pn;
     uint32_t pph, pbuf;
@@ -394,7 +400,7 @@ template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(cons
     if (c.pn < 0) return;
     const int pn = c.pn, psg = c.psg, N = a.g.N;
     c.pn = -1;
-    umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
+    umma::mbar_wait(&c.bars[kZDone], c.pph & 1);      // part 1's z_done arrival of that step (acquire of its zsm store)
     if (!c.live) return;
     float4 pz = c.pz;
 #pragma unroll
@@ -443,15 +449,15 @@ template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(cons
 // probability head without FP64: log-softmax term of the pending top-layer step in FP32 (log1pf / expf, ~1e-7 relative, the same
 // numbers finish_head casts to double), accumulated with Kahan compensation.  FLIP: term - base term, both FP32 numbers of nearly
 // equal magnitude, so the difference is (almost always) exact.
-// LATE: called two steps after the top-layer step instead of one.  Its c_done phase is then two phases back -- a parity wait on it
-// would alias the phase in progress -- and the wait is not needed: this thread has passed the commit barrier of the current step,
-// whose MMAs were issued after every row thread had released the accumulators of the step before, i.e. after every c_done arrival
-// of the top-layer step (the barrier chain carries the acquire of part 1's zsm store).
+// LATE: called two steps after the top-layer step instead of one.  No wait is needed: this thread has passed the commit barrier of
+// the current step, whose MMAs were issued after every row thread had released the accumulators of the step before (kAccFree cannot
+// be over-arrived: a thread drains step g + 1 only after phase g has completed), i.e. after every thread had finished the top-layer
+// step (the barrier chain carries the acquire of part 1's zsm store).
 template <bool BASE, bool LATE = false> __device__ __forceinline__ void finish_head_f32(const Args& a, Ctx& c) {
     if (c.pn < 0) return;
     const int pn = c.pn, psg = c.psg;
     c.pn = -1;
-    if (!LATE) umma::mbar_wait(&c.bars[kCDone], c.pph & 1);      // part 1's c_done arrival of that step (acquire of its zsm store)
+    if (!LATE) umma::mbar_wait(&c.bars[kZDone], c.pph & 1);      // part 1's z_done arrival of that step (acquire of its zsm store)
     if (!c.live) return;
     float4 o = c.zsm[c.pbuf * (kParts - 1) * kRows + c.rowi];
     if constexpr (kParts == 3) {
@@ -479,16 +485,14 @@ template <bool BASE, bool LATE = false> __device__ __forceinline__ void finish_h
 // What the backward recurrence of one unit needs from the forward pass, as five factors of d h (gru_tc16b.cuh):
 //   u: d h_{n-1} += d h * u;   alpha = (1-u)(1-c^2): d a_c = d h * alpha;   beta = (h_prev - c) u (1-u): d a_u = d h * beta;
 //   gamma = alpha * aq * r (1-r): d a_r = d h * gamma;   rho = alpha * r: d aq = d h * rho         (aq = h Kch + bch = dq / (2 log2 e))
-// The stash keeps them as [factor][unit][row] (a warp's 32 rows are one 128-byte store; [factor][row][unit] with 8-byte stores per
-// unit pair was measured 2.4x slower: 32 sectors per store instruction instead of 4-5).
-__device__ __forceinline__ void store_bwd_factors(float* gs, size_t AS, float u, float r, float c, float dq, float hprev) {
+// A (tile, site, layer) block of the stash is [unit][row][u, alpha, beta, gamma] followed by [unit][row] rho: a row thread writes a
+// unit with one 16-byte and one 4-byte store, a warp's 32 rows are 512 + 128 contiguous bytes (five 4-byte stores per unit into
+// [factor][unit][row] cost 21 ms per stash pass at cfg2, 8-byte stores into [factor][row][unit] 50 ms: 32 sectors per instruction).
+__device__ __forceinline__ void store_bwd_factors(float* g4, float* grho, float u, float r, float c, float dq, float hprev) {
     const float aq = dq * 0.34657359027997264f;            // 1 / (2 log2 e): the candidate rows of the images are pre-scaled
     const float al = (1.0f - u) * (1.0f - c * c);
-    gs[0] = u;
-    gs[AS] = al;
-    gs[2 * AS] = (hprev - c) * u * (1.0f - u);
-    gs[3 * AS] = al * aq * r * (1.0f - r);
-    gs[4 * AS] = al * r;
+    *reinterpret_cast<float4*>(g4) = make_float4(u, al, (hprev - c) * u * (1.0f - u), al * aq * r * (1.0f - r));
+    *grho = al * r;
 }
 
 // reset / update gates 1/(1 + 2^a) of two units, in place.  RNNWF_GATES selects how many reciprocals are shared (MUFU pipe against
@@ -658,10 +662,10 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
 #else
                     f2_split(cc, cs0, cs1);
 #endif
-                    const size_t AS = (size_t)H * Mold;
-                    float* gs = a.gstore + ((((c.rowbase + n) * L + l) * 5) * (size_t)H + kPU * part + jl) * Mold + c.m;
-                    store_bwd_factors(gs, AS, uu[jl], rr[jl], cs0, dq[jl], hp[jl]);
-                    store_bwd_factors(gs + Mold, AS, uu[jl + 1], rr[jl + 1], cs1, dq[jl + 1], hp[jl + 1]);
+                    float* blk = a.gstore + ((c.rowbase + n) * L + l) * 5 * (size_t)H * Mold;          // [unit][row][4] | [unit][row]
+                    const size_t ur = (size_t)(kPU * part + jl) * Mold + c.m;
+                    store_bwd_factors(blk + 4 * ur, blk + 4 * (size_t)H * Mold + ur, uu[jl], rr[jl], cs0, dq[jl], hp[jl]);
+                    store_bwd_factors(blk + 4 * (ur + Mold), blk + 4 * (size_t)H * Mold + ur + Mold, uu[jl + 1], rr[jl + 1], cs1, dq[jl + 1], hp[jl + 1]);
                 }
             }
             hp[jl] = h0;
@@ -702,11 +706,13 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
             c.p_la = la_n;
             c.p_ph = ph_n;
             c.p_laf = la_nf;
-            c.pph = c.cda;
+            c.pph = c.zc;
             c.pbuf = par;
         } else {
             c.zsm[(par * (kParts - 1) + (part - 1)) * kRows + c.rowi] = make_float4(z0, z1, y0, y1);
+            umma::mbar_arrive(&c.bars[kZDone]);
         }
+        ++c.zc;
     }
     umma::wait_st();
     umma::fence_before_sync();
@@ -867,7 +873,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
     const int part = warp >> 2, rowi = tid & 127;
     const int total = (BASE ? 1 : a.nslots) * a.tiles128;
     bool weights_ready = false;
-    uint32_t gstep = 0, cdp = 0;             // steps done so far; c_done phases used so far (one per step + one per chain)
+    uint32_t gstep = 0, cdp = 0, ztop = 0;   // steps done so far; c_done phases used so far (one per step + one per chain); top-layer steps so far
     while (true) {
         if (tid == 0) *s_work = atomicAdd(a.counter, 1);
         __syncthreads();
@@ -898,7 +904,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
             if constexpr (ROW) {
                 Ctx c;
                 c.tab = tab; c.zsm = zsm; c.bars = bars; c.lane_addr = lane_addr; c.rowi = rowi; c.m = m; c.part = part; c.live = live;
-                c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.acc = acc; c.acc_im = acc_im;
+                c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.zc = ztop; c.acc = acc; c.acc_im = acc_im;
                 c.pz = make_float4(0.f, 0.f, 0.f, 0.f); c.psg = 0; c.pn = -1; c.pph = 0; c.pbuf = 0; c.nup = 0; c.p_la = 0.0; c.p_ph = 0.0; c.p_laf = 0.f; c.accf = 0.f; c.compf = 0.f;
                 TCP_T(c.w_ru = c.w_c = c.t_ru = c.t_c = 0; long long ch0 = clock64();)
                 row_chain<BASE, CPLX>(a, c);
@@ -939,6 +945,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
             }
             gstep += (uint32_t)nsteps;
             cdp += (uint32_t)nsteps + 1;
+            ztop += (uint32_t)(N - n0);
         }
         if (live && part == 0) {
             if (BASE) {
@@ -973,6 +980,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         umma::mbar_init(&bars[kAccFree], kRowThreads);
         umma::mbar_init(&bars[kCDone], kRowThreads);
         umma::mbar_init(&bars[kWImg], 1);
+        umma::mbar_init(&bars[kZDone], kRowThreads - kRows);
         umma::mbar_fence_init();
     }
     umma::fence_before_sync();
