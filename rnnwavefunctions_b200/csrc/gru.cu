@@ -304,6 +304,23 @@ static int chain_mode(const GruLayout& g) {
     return tc16p::supported_padded(g) ? 3 : 0;
 }
 
+// Sampler selection (FP32 stacks the tensor-core kernel covers): default tcgen05 (tc16p::chain_kernel<.., SAMPLE>), RNNWF_SAMPLER=ffma
+// keeps the CUDA-core tile engine (A/B measurements, cross-checks)
+static bool sampler_tc(const GruLayout& g) {
+    const char* e = getenv("RNNWF_SAMPLER");
+    if (e && strcmp(e, "ffma") == 0) return false;
+    return tc16p::supported_padded(g);
+}
+struct SampleTcWs { uint8_t* sampT; unsigned char* img; int* counter; int tiles128; };
+static SampleTcWs carve_sample_tc(Ws& ws, const GruLayout& g, int64_t ns) {
+    SampleTcWs w;
+    w.tiles128 = (int)cdiv(ns, tc16p::kRows);
+    w.sampT = ws.take<uint8_t>((size_t)w.tiles128 * tc16p::kRows * g.N);
+    w.img = ws.take<unsigned char>(tc16_img_bytes(g));
+    w.counter = ws.take<int>(4);
+    return w;
+}
+
 // ---------------------------------------------------------------------------------------------
 // typed implementations behind the C ABI
 // ---------------------------------------------------------------------------------------------
@@ -318,6 +335,13 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
     Ws ws(nullptr, 0);
     switch (op) {
         case RNNWF_OP_SAMPLE:
+            if (std::is_same<T, float>::value && tc16p::supported_padded(g)) {   // whichever sampler RNNWF_SAMPLER picks at run time fits
+                Ws w2(nullptr, 0);
+                carve_sample_tc(w2, g, ns);
+                carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns);
+                ws.used = std::max(ws.used, w2.used);
+                break;
+            }
         case RNNWF_OP_LOGPSI: carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns); break;
         case RNNWF_OP_TFIM_ELOC:
             carve_gru<T>(ws, carve_layout<T>(g), c, tiles, true, g.N, cplx, ns);
@@ -344,6 +368,17 @@ template <typename T>
 int gru_sample_t(const rnnwf_model& m, const void* params, int64_t ns, uint64_t seed, uint64_t off, uint8_t* out, void* wsp,
                  size_t wsb, cudaStream_t s) {
     const GruLayout g = make_gru_layout(m);
+    if constexpr (std::is_same<T, float>::value) {
+        if (sampler_tc(g)) {
+            Ws ws(wsp, wsb);
+            SampleTcWs w = carve_sample_tc(ws, g, ns);
+            RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
+            if (int e = tc16p::launch_sample(g, w.tiles128, (const float*)params, w.img, w.sampT, w.counter, seed, off, s)) return e;
+            prof_count(); samp_untranspose_kernel<<<grid_for(ns * g.N), 256, 0, s>>>(w.sampT, out, ns, g.N, tc16p::kRows);
+            RNNWF_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     const GruLaunch c = choose_gru_launch<T>(g, ns, 1);
     RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
     const bool cplx = m.head == RNNWF_HEAD_COMPLEX;

@@ -355,6 +355,8 @@ struct Args {
     int* counter;
     // complex cRNN / J1-J2 exchanges (CPLX instantiations): phases, imaginary parts, slot plan
     double *ph_sel, *ph_oth, *lp_im, *delta_im;
+    uint8_t* sampT;           // SAMPLE: drawn configurations [tile][site][128]
+    uint64_t seed, sample_offset;   // SAMPLE: Philox key, global id of row 0
     const int* order;         // slots by decreasing chain length
     const double *j1, *j2;    // couplings: slots with a zero coupling are skipped (J1J2/TrainingRNN_J1J2.py:69,84)
     int n_kind1, n_kind2, nslots;
@@ -544,7 +546,9 @@ __device__ __forceinline__ void ru_pair(float& r0, float& u0, float& r1, float& 
 // one (site n, layer l) step of a row thread: pull the step's accumulators out of TMEM, release them to the MMA warp, then
 // reset / update gates, candidate, new state, head partial sums and restaging from registers.
 // hp: this thread's 25 units of h^l (previous site in, this site out).
-template <bool BASE, bool CPLX, int LS = -1>
+// SAMPLE (with BASE): the autoregressive sampler -- no teacher forcing, nothing stashed; the top-layer step ends with the draw of
+// sigma_n (part 0: head, Philox uniform keyed by (global sample id, site), one-hot input of site n + 1), see row_chain_sample.
+template <bool BASE, bool CPLX, int LS = -1, bool SAMPLE = false>
 __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn, float* hp) {
     constexpr int H = 50;
     const int L = LS >= 0 ? 3 : a.g.L, l = LS >= 0 ? LS : l_dyn;      // LS >= 0: the statically specialised copies of a 3-layer stack
@@ -558,7 +562,9 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     double la_n = 0.0, ph_n = 0.0;
     float la_nf = 0.f;
     // (part 0 finishes the head, part 1 stages the one-hot input: the two warps of an SM sub-partition carry similar extra work)
-    if (c.live && ((part == 0 && top) || (part == 1 && l == 0))) {
+    float u_n = 0.f;
+    if (SAMPLE && top && part == 0) u_n = philox_uniform(a.seed, a.sample_offset + (uint64_t)(c.rowbase / (size_t)N) * Mold + c.m, (uint32_t)n);   // global sample id: the draws do not depend on the sharding
+    if (!SAMPLE && c.live && ((part == 0 && top) || (part == 1 && l == 0))) {
         spin_n = a.sigT[(c.rowbase + n) * Mold + c.m];   // raw: the flip of a modified site is applied where the value is used, after
                                                          // the gate math -- nothing before the accumulator drain may wait on this load
         if (!BASE && top && part == 0) {
@@ -593,7 +599,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     umma::fence_before_sync();
     umma::mbar_arrive(&c.bars[kAccFree]);              // the accumulators may be overwritten by the next step's MMAs
     TCP_T(long long t2 = clock64(); c.w_c += t2 - t1;)
-    if (part == 0) {
+    if (!SAMPLE && part == 0) {
         // the pending head of the last top-layer step.  Three-layer copies: finished in the bottom-layer step, the shortest of the
         // three and the one the top layer's MMAs run under (ncu: the top-layer copy waited 11 % of its time at the commit barrier);
         // the middle-layer step only takes it when no bottom-layer step follows on this anti-diagonal (the last two of a chain)
@@ -614,7 +620,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     // ---- candidate, new state, head partial sums, restaging
     const uint32_t reg = c.lane_addr + kColR + 64 * l + (kPU / 2) * part;
     const float* tab = c.tab + 2 * kUP * part;
-    float* hst = BASE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kPU * part) * Mold + c.m : nullptr;
+    float* hst = BASE && !SAMPLE ? a.hstore + (((c.rowbase + n) * L + l) * (size_t)H + kPU * part) * Mold + c.m : nullptr;
     float y0 = 0.f, y1 = 0.f;
     f2_t z01 = f2_make(0.f, 0.f);                      // head partial sums (z0, z1), one packed FMA per unit
 #pragma unroll
@@ -654,7 +660,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
 #endif
             f2_split(f2_fma(f2_make(uu[jl], uu[jl + 1]), f2_sub(f2_make(hp[jl], hp[jl + 1]), cc), cc), h0, h1);
 #endif
-            if constexpr (BASE) {
+            if constexpr (BASE && !SAMPLE) {
                 if (a.gstore != nullptr && c.live) {   // gradient's stash pass: the factors of the backward recurrence (hp still holds h_prev)
                     float cs0, cs1;
 #if RNNWF_CAND < 2
@@ -681,7 +687,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
                     y1 = fmaf(h1, tab[132 + 2 * jl + 3], y1);
                 }
             }
-            if (BASE && c.live) {
+            if (BASE && !SAMPLE && c.live) {
                 hst[(size_t)jl * Mold] = h0;
                 hst[(size_t)(jl + 1) * Mold] = h1;
             }
@@ -691,7 +697,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
         else stage_tail(reg + 4 * kG8, hp + 8 * kG8, part);
     }
     if (!BASE && (n == c.s || n == c.t)) spin_n = 1 - spin_n;
-    if (part == 1 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
+    if (!SAMPLE && part == 1 && l == 0 && n + 1 < N) {            // one-hot input of (n + 1, 0): the spin of site n (M(n, 0) has completed)
         const int code = c.live ? spin_n : 2;
         const float oh[1] = {__uint_as_float(pack_h2(code == 0 ? 1.f : 0.f, code == 1 ? 1.f : 0.f))};
         umma::tmem_st1(c.lane_addr + kColR + 64 * L, oh);
@@ -699,7 +705,37 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     if (top) {   // partial head sums; part 0 finishes the log-softmax at its next step (or after the chain)
         float z0, z1;
         f2_split(z01, z0, z1);
-        if (part == 0) {
+        if constexpr (SAMPLE) {
+            // draw sigma_n (1DTFIM/RNNwavefunction.py:65-70; U(1) mask J1J2/ComplexRNNwavefunction.py:85-95): P(0) of the 2-way softmax
+            // in FP32, sigma = (u >= P(0)), the convention of gru_sample_kernel and of the oracle
+            if (part != 0) {
+                c.zsm[(par * (kParts - 1) + (part - 1)) * kRows + c.rowi] = make_float4(z0, z1, y0, y1);
+                umma::mbar_arrive(&c.bars[kZDone]);
+            } else {
+                umma::mbar_wait(&c.bars[kZDone], c.zc & 1);
+#pragma unroll
+                for (int q = 0; q < kParts - 1; ++q) {
+                    const float4 o = c.zsm[(par * (kParts - 1) + q) * kRows + c.rowi];
+                    z0 += o.x; z1 += o.y;
+                }
+                z0 += c.tab[128]; z1 += c.tab[129];
+                const float p0 = 1.0f / (1.0f + expf(z1 - z0));
+                int sg = u_n >= p0 ? 1 : 0;
+                if (CPLX && 2 * n >= N) {
+                    const int half = N / 2, ndn = n - c.nup;
+                    const bool ok_dn = (half - 1 - ndn) >= 0, ok_up = (half - 1 - c.nup) >= 0;
+                    if (!ok_up) sg = 0;
+                    else if (!ok_dn) sg = 1;
+                }
+                c.nup += sg;
+                a.sampT[(c.rowbase + n) * Mold + c.m] = (uint8_t)sg;
+                if (n + 1 < N) {
+                    const float oh[1] = {__uint_as_float(pack_h2(sg == 0 ? 1.f : 0.f, sg == 1 ? 1.f : 0.f))};
+                    umma::tmem_st1(c.lane_addr + kColR + 64 * L, oh);
+                }
+            }
+            ++c.zc;
+        } else if (part == 0) {
             c.pz = make_float4(z0, z1, y0, y1);
             c.pn = n;
             c.psg = spin_n;
@@ -712,7 +748,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
             c.zsm[(par * (kParts - 1) + (part - 1)) * kRows + c.rowi] = make_float4(z0, z1, y0, y1);
             umma::mbar_arrive(&c.bars[kZDone]);
         }
-        ++c.zc;
+        if constexpr (!SAMPLE) ++c.zc;
     }
     umma::wait_st();
     umma::fence_before_sync();
@@ -796,6 +832,43 @@ __device__ __forceinline__ void row_chain(const Args& a, Ctx& c) {
     }
 }
 
+// all row-thread work of the sampler on one tile: sites in order, layers bottom-up (site n + 1 needs the draw of site n, so there
+// are no anti-diagonals to walk and every step consumes the output of the step before it)
+template <bool CPLX>
+__device__ __forceinline__ void row_chain_sample(const Args& a, Ctx& c) {
+    const int L = a.g.L, N = a.g.N, part = c.part;
+    float hA[kUP], hB[kUP], hC[kUP];       // layers 0, 1, 2
+#pragma unroll
+    for (int j = 0; j < kUP; ++j) { hA[j] = 0.f; hB[j] = 0.f; hC[j] = 0.f; }
+    const uint32_t regp = c.lane_addr + kColR + (kPU / 2) * part;
+    stage_all(regp, hA, part);
+    if (L > 1) stage_all(regp + 64, hB, part);
+    if (L > 2) stage_all(regp + 128, hC, part);
+    c.pn = -1;
+    c.nup = 0;
+    if (part == 0) {                       // the input of site 0 is the zero vector
+        const float oh[1] = {0.f};
+        umma::tmem_st1(c.lane_addr + kColR + 64 * L, oh);
+    }
+    umma::wait_st();
+    umma::fence_before_sync();
+    umma::mbar_arrive(&c.bars[kCDone]);                // "step -1": operands staged
+    ++c.cda;
+#pragma unroll 1
+    for (int n = 0; n < N; ++n) {
+        if (L == 3) {
+            row_step<true, CPLX, 0, true>(a, c, n, 0, hA);
+            row_step<true, CPLX, 1, true>(a, c, n, 1, hB);
+            row_step<true, CPLX, 2, true>(a, c, n, 2, hC);
+        } else if (L == 2) {
+            row_step<true, CPLX, -1, true>(a, c, n, 0, hA);
+            row_step<true, CPLX, -1, true>(a, c, n, 1, hB);
+        } else {
+            row_step<true, CPLX, -1, true>(a, c, n, 0, hA);
+        }
+    }
+}
+
 // the MMA instructions of one (site, layer) step; executed by every lane of the (converged) MMA warp, one elected lane issues.
 // x group: D[cx | r | u | 4] = x * X^T (overwrite), h group: D[r | u | ch | junk] += h * H^T, where the very first h
 // instruction is split in two because it accumulates onto r, u but must overwrite ch.  Consecutive instructions reuse the A chunk
@@ -864,7 +937,7 @@ struct Dbg { long long wru, wc, tru, tc, chain, mw1, mw2, mi; int nch; };
 
 // the persistent work loop of one warp role (ROW: the 8 row warps; otherwise the MMA warp).  Both roles execute the same
 // sequence of CTA barriers; they are separate instantiations so that each runs under its own register budget (setmaxnreg).
-template <bool BASE, bool CPLX, bool ROW, bool IDLE = false>
+template <bool BASE, bool CPLX, bool ROW, bool IDLE = false, bool SAMPLE = false>
 __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, float4* zsm, uint64_t* bars, int* s_work, uint32_t tbase,
                                               uint32_t lane_addr, uint32_t sB, Dbg& dbg) {
     const Layout& t = a.t;
@@ -907,7 +980,8 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
                 c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.zc = ztop; c.acc = acc; c.acc_im = acc_im;
                 c.pz = make_float4(0.f, 0.f, 0.f, 0.f); c.psg = 0; c.pn = -1; c.pph = 0; c.pbuf = 0; c.nup = 0; c.p_la = 0.0; c.p_ph = 0.0; c.p_laf = 0.f; c.accf = 0.f; c.compf = 0.f;
                 TCP_T(c.w_ru = c.w_c = c.t_ru = c.t_c = 0; long long ch0 = clock64();)
-                row_chain<BASE, CPLX>(a, c);
+                if constexpr (SAMPLE) row_chain_sample<CPLX>(a, c);
+                else row_chain<BASE, CPLX>(a, c);
                 acc = c.acc; acc_im = c.acc_im;
                 TCP_T(dbg.wru += c.w_ru; dbg.wc += c.w_c; dbg.tru += c.t_ru; dbg.tc += c.t_c; dbg.chain += clock64() - ch0; ++dbg.nch;)
             } else {   // MMA warp: all lanes stay converged, one elected lane issues
@@ -915,6 +989,25 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
                 uint32_t g = gstep, cdw = cdp;
                 int pn = -1000, pl = -1;
                 TCP_T(long long m_w1 = 0, m_w2 = 0, m_i = 0;)
+                if constexpr (SAMPLE) {   // sites in order, layers bottom-up: every step waits for the restaged output of the step before it
+#pragma unroll 1
+                    for (int n = 0; n < N; ++n) {
+#pragma unroll 1
+                        for (int l = 0; l < L; ++l) {
+                            const uint32_t lb = sB + (l == 0 ? 0u : (uint32_t)(t.l0_bytes + (l - 1) * t.l1_bytes));
+                            const uint32_t h_hi = lb, h_lo = lb + t.im_bytes, x_hi = lb + t.im_bytes + t.im2_bytes;
+                            const uint32_t x_lo = x_hi + (l == 0 ? t.im0_bytes : t.im_bytes);
+                            const uint32_t rX = tbase + kColR + 64 * (l == 0 ? L : l - 1), rH = tbase + kColR + 64 * l;
+                            umma::mbar_wait(&bars[kAccFree], (g - 1) & 1);
+                            umma::mbar_wait(&bars[kCDone], cdw & 1);
+                            umma::fence_after_sync();
+                            issue_step(tbase, rX, rH, x_hi, x_lo, h_hi, h_lo, l == 0);
+                            umma::commit_elect(&bars[kFull]);
+                            ++g;
+                            ++cdw;
+                        }
+                    }
+                } else
 #pragma unroll 1
                 for (int d = n0; d <= N - 1 + L - 1; ++d) {
 #pragma unroll 1
@@ -947,7 +1040,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
             cdp += (uint32_t)nsteps + 1;
             ztop += (uint32_t)(N - n0);
         }
-        if (live && part == 0) {
+        if (!SAMPLE && live && part == 0) {
             if (BASE) {
                 a.lp[t120 * Mold + m] = acc;
                 if (CPLX) a.lp_im[t120 * Mold + m] = acc_im;
@@ -960,7 +1053,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
     return gstep;
 }
 
-template <bool BASE, bool CPLX>
+template <bool BASE, bool CPLX, bool SAMPLE = false>
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(128) unsigned char smem_p16[];
     const Layout& t = a.t;
@@ -1016,11 +1109,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     uint32_t gstep;
     if (is_row) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRowRegs));
-        gstep = work_loop<BASE, CPLX, true>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
+        gstep = work_loop<BASE, CPLX, true, false, SAMPLE>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
-        if (warp == kMmaWarp) gstep = work_loop<BASE, CPLX, false>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
-        else gstep = work_loop<BASE, CPLX, false, true>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);   // CTA barriers only
+        if (warp == kMmaWarp) gstep = work_loop<BASE, CPLX, false, false, SAMPLE>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);
+        else gstep = work_loop<BASE, CPLX, false, true, SAMPLE>(a, tab, zsm, bars, s_work, tbase, lane_addr, sB, dbg);   // CTA barriers only
     }
     TCP_T(if (gstep > 0 && !BASE) {
         const long long tot = clock64() - k_t0;
@@ -1090,6 +1183,31 @@ static int launch_eloc(const GruLayout& greal, int Mold, int tiles, const float*
     a.gstore = gstore;
     prof_count(); pack_kernel<<<148, 256, 0, s>>>(greal, a.t, params, img);
     return launch_chains<false>(a, sms, flips, s);
+}
+
+// autoregressive sampler (probability head, or the cRNN's amplitude head with the U(1) mask): 128-row tiles, one persistent CTA each
+static int launch_sample(const GruLayout& greal, int tiles128, const float* params, unsigned char* img, uint8_t* sampT, int* counter,
+                         uint64_t seed, uint64_t sample_offset, cudaStream_t s) {
+    int sms;
+    const GruLayout g = padded_layout(greal);
+    Args a = make_args(g, kRows, tiles128, img, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, counter, sms);
+    a.sampT = sampT; a.seed = seed; a.sample_offset = sample_offset;
+    const int smem = (int)smem_bytes(a.t);
+    RNNWF_CHECK(smem <= kSmemLimit, -3, "tensor-core sampler needs %d bytes of shared memory", smem);
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(greal, a.t, params, img);
+    RNNWF_CUDA(cudaMemsetAsync(a.counter, 0, sizeof(int), s));
+    prof_count();
+    if (g.nheads == 2) {
+        auto k = chain_kernel<true, true, true>;
+        RNNWF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<std::min(a.tiles128, sms), kThreads, smem, s>>>(a);
+    } else {
+        auto k = chain_kernel<true, false, true>;
+        RNNWF_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<std::min(a.tiles128, sms), kThreads, smem, s>>>(a);
+    }
+    RNNWF_CUDA(cudaGetLastError());
+    return 0;
 }
 
 // base pass + NN / NNN exchange chains of the complex cRNN (J1-J2); `order` lists the 2N-3 slots by decreasing chain length

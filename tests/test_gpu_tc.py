@@ -182,3 +182,66 @@ def test_narrower_stacks_run_zero_padded_on_the_tensor_core_kernel(H, L, N, ns):
         e, la = ops.j1j2_eloc(mc, fc, u8(sc), J1, J2, Bz, marshall_sign=True)
         refc = O.j1j2_local_energies(J1, J2, Bz, sc, lambda c: O.crnn_log_amplitude(pc, c), marshall_sign=True)
         assert np.abs(e.cpu().numpy() - refc).max() < 3e-5 * max(1.0, np.abs(refc).max())
+
+
+@pytest.mark.parametrize("L", [2, 3])
+def test_repeated_calls_are_bitwise_identical(L):
+    """Every kernel on the path is deterministic (no atomics in the arithmetic, fixed reduction orders), so identical calls must agree
+    bit for bit.  This is the regression test of a hand-off race of the pipelined chain kernel: the head partial sums of the second
+    row thread of a sample were read behind a barrier that counts arrivals, which a warp running one step ahead could complete early
+    (seen as 32 wrong log-probability terms at site N - 2 in about one of ten stash passes of the gradient at 10^4 samples)."""
+    N, ns = 96, 10000
+    from rnnwavefunctions_b200 import params as P
+    model = ops.make_model(num_layers=L, units=50, n_sites=N)
+    flat = torch.tensor(P.init_flat(P.gru_shapes([50] * L), 7 + L, np.float32), device=dev())
+    s = ops.sample(model, flat, ns, seed=5)
+    w = torch.randn(ns, dtype=torch.float64, device=dev(), generator=torch.Generator(device=dev()).manual_seed(3)) / ns
+    g0 = ops.vmc_grad(model, flat, s, w).clone()
+    e0, lp0 = (t.clone() for t in ops.tfim_eloc(model, flat, s, np.ones(N), 1.0))
+    for _ in range(12):
+        assert torch.equal(ops.vmc_grad(model, flat, s, w), g0)
+    for _ in range(3):
+        e, lp = ops.tfim_eloc(model, flat, s, np.ones(N), 1.0)
+        assert torch.equal(lp, lp0) and torch.equal(e, e0)
+
+
+def sample_with(sampler, model, flat, ns, **kw):
+    old = os.environ.get("RNNWF_SAMPLER")
+    if sampler:
+        os.environ["RNNWF_SAMPLER"] = sampler
+    else:
+        os.environ.pop("RNNWF_SAMPLER", None)
+    try:
+        return ops.sample(model, flat, ns, **kw).cpu().numpy().astype(np.int64)
+    finally:
+        if old is None:
+            os.environ.pop("RNNWF_SAMPLER", None)
+        else:
+            os.environ["RNNWF_SAMPLER"] = old
+
+
+@pytest.mark.parametrize("L,N,ns", [(1, 20, 700), (2, 33, 300), (3, 24, 700), (3, 130, 200)])
+def test_tensor_core_sampler_draws_follow_the_oracle_conditionals(L, N, ns):
+    """tc16p::chain_kernel<.., SAMPLE> (1DTFIM/RNNwavefunction.py:35-74): every draw is sigma_n = (u_n >= P(0 | sigma_<n)) with the
+    Philox uniform of (global sample id, site) unless u is within 1e-5 of the threshold; rows do not depend on the sharding; the
+    CUDA-core sampler gives (nearly always) the same rows."""
+    units = [50] * L
+    p = O.randomize_biases(O.init_gru_params(units, seed=10 + L, dtype=np.float32, scale=2.0), seed=L + 1)
+    model = ops.make_model(num_layers=L, units=50, n_sites=N)
+    flat = torch.tensor(O.flatten(p), device=dev())
+    seed, off = 4321, 777
+    s = sample_with(None, model, flat, ns, seed=seed, sample_offset=off)
+    assert s.shape == (ns, N) and set(np.unique(s)) <= {0, 1}
+    probs = O.gru_conditionals(p, s)
+    ids = np.arange(ns, dtype=np.uint64) + np.uint64(off)
+    bad = 0
+    for n in range(N):
+        u = O.philox_uniform(seed, ids, n)
+        want = (u >= probs[:, n, 0]).astype(np.int64)
+        near = np.abs(u - probs[:, n, 0]) < 1e-5
+        bad += int(((want != s[:, n]) & ~near).sum())
+    assert bad == 0
+    s2 = sample_with(None, model, flat, min(150, ns - 100), seed=seed, sample_offset=off + 100)   # another split, a partly filled tile
+    assert np.array_equal(s2, s[100:250])
+    sf = sample_with("ffma", model, flat, ns, seed=seed, sample_offset=off)
+    assert (sf == s).all(axis=1).mean() > 0.99
