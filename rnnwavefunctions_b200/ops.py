@@ -5,6 +5,7 @@ PyTorch is plumbing here: it owns device memory and streams.  All arithmetic hap
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -85,6 +86,67 @@ def _ws_for(model, op, ns, flags, device):
     return _WS.get(n, device), n
 
 
+def workspace_bytes(model, op, ns, flags=0) -> int:
+    return int(_lib.load().rnnwf_workspace_bytes(C.byref(model), op, int(ns), flags))
+
+
+def workspace_budget(device) -> int:
+    """Bytes one call may use for its workspace: RNNWF_WS_BUDGET_GB, else 80 % of the device memory that is free or already held by
+    this module's scratch buffer."""
+    env = os.environ.get("RNNWF_WS_BUDGET_GB")
+    if env:
+        return int(float(env) * 2 ** 30)
+    free, _ = torch.cuda.mem_get_info(device)
+    held = _WS.buf.get(str(device))
+    return int(0.8 * (free + (held.numel() if held is not None else 0)))
+
+
+def sample_chunk(model, op, ns, flags, device) -> int:
+    """Largest number of samples per call whose workspace fits the budget.  The E_loc stash grows as ns * N * L * H and the gradient
+    scratch is ~7x that (47 GB for 10^4 samples at N = 1000, 3 x 50), so large batches are evaluated in slices, as the reference
+    evaluates its queue of (N + 1) * ns configurations in chunks of `numsamples` (1DTFIM/TrainingRNN_1DTFIM.py:56-72).  Samples are
+    independent (E_loc) or enter linearly (gradient): slicing changes nothing but the order of the gradient's final sum."""
+    ns = int(ns)
+    if ns <= 256:
+        return ns
+    need = workspace_bytes(model, op, ns, flags)
+    held = _WS.buf.get(str(device))
+    if held is not None and need <= held.numel():      # fits the scratch buffer this module already holds: no device query
+        return ns
+    budget = workspace_budget(device)
+    if need <= budget:
+        return ns
+    lo, hi = 1, ns // 256                       # multiples of 256 rows (whole 128-row tiles in both directions of the parity model)
+    while lo < hi:
+        mid = (lo + hi + 1) // 2
+        if workspace_bytes(model, op, mid * 256, flags) <= budget:
+            lo = mid
+        else:
+            hi = mid - 1
+    return lo * 256
+
+
+def _sliced(fn):
+    """Decorator for the per-sample ops: evaluate `samples_u8` (positional argument 2) in slices that fit the workspace budget and
+    concatenate the per-sample results."""
+    import functools
+    import inspect
+    sig = inspect.signature(fn)
+
+    @functools.wraps(fn)
+    def wrapped(model, params, samples_u8, *args, **kw):
+        ns = samples_u8.shape[0]
+        flags = sig.bind(model, params, samples_u8, *args, **kw).arguments.get("flags", 0)
+        step = sample_chunk(model, wrapped.op, ns, flags, params.device)
+        if step >= ns:
+            return fn(model, params, samples_u8, *args, **kw)
+        parts = [fn(model, params, samples_u8[i:i + step].contiguous(), *args, **kw) for i in range(0, ns, step)]
+        if isinstance(parts[0], tuple):
+            return tuple(None if col[0] is None else torch.cat(col) for col in zip(*parts))
+        return torch.cat(parts)
+    return wrapped
+
+
 def _check_params(model, params):
     if not params.is_cuda or params.dtype != torch_dtype(model) or not params.is_contiguous():
         raise ValueError("params must be a contiguous CUDA tensor of the model dtype")
@@ -114,6 +176,15 @@ def sample(model, params, ns, seed=0, sample_offset=0):
     return out
 
 
+def _op(op):
+    def deco(fn):
+        w = _sliced(fn)
+        w.op = op
+        return w
+    return deco
+
+
+@_op(OP_LOGPSI)
 @_on_device_of(1)
 def logpsi(model, params, samples_u8, flags=0):
     """-> float64 [ns] (probability head) or complex128 [ns] (complex head)."""
@@ -126,6 +197,7 @@ def logpsi(model, params, samples_u8, flags=0):
     return torch.view_as_complex(out) if cplx else out
 
 
+@_op(OP_TFIM_ELOC)
 @_on_device_of(1)
 def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
     _check_params(model, params)
@@ -139,6 +211,7 @@ def tfim_eloc(model, params, samples_u8, jz, bx, flags=0, want_logp=True):
     return eloc, logp
 
 
+@_op(OP_TFIM_ELOC)
 @_on_device_of(1)
 def tfim_flip_ratios(model, params, samples_u8, jz, bx, flags=0):
     """-> (eloc [ns], logp [ns], ratios [ns, N]) with ratios[s, k] = psi(sigma_s, site k flipped) / psi(sigma_s) (rnnwf_tfim_flip_ratios)."""
@@ -190,6 +263,7 @@ def j1j2_enumerate(samples_u8, j1, j2, bz, periodic=False, marshall_sign=False, 
     return sig, el, cnt
 
 
+@_op(OP_J1J2_ELOC)
 @_on_device_of(1)
 def j1j2_eloc(model, params, samples_u8, j1, j2, bz, marshall_sign=False, want_logpsi=True):
     _check_params(model, params)
@@ -204,9 +278,22 @@ def j1j2_eloc(model, params, samples_u8, j1, j2, bz, marshall_sign=False, want_l
     return torch.view_as_complex(eloc), (torch.view_as_complex(lpsi) if want_logpsi else None)
 
 
-@_on_device_of(1)
 def vmc_grad(model, params, samples_u8, weights, flags=0):
-    """weights: float64 [ns] (probability head) or complex128 / float64 [ns,2] (complex head). -> float64 [P]."""
+    """weights: float64 [ns] (probability head) or complex128 / float64 [ns,2] (complex head). -> float64 [P].
+    The gradient is linear in the per-sample weights: batches whose scratch does not fit the workspace budget are summed slice by slice."""
+    ns = samples_u8.shape[0]
+    step = sample_chunk(model, OP_VMC_GRAD, ns, flags, params.device)
+    if step >= ns:
+        return _vmc_grad(model, params, samples_u8, weights, flags)
+    total = None
+    for i in range(0, ns, step):
+        g = _vmc_grad(model, params, samples_u8[i:i + step].contiguous(), weights[i:i + step], flags)
+        total = g.clone() if total is None else total.add_(g)
+    return total
+
+
+@_on_device_of(1)
+def _vmc_grad(model, params, samples_u8, weights, flags=0):
     _check_params(model, params)
     ns = samples_u8.shape[0]
     ws, nb = _ws_for(model, OP_VMC_GRAD, ns, flags, params.device)

@@ -245,3 +245,37 @@ def test_tensor_core_sampler_draws_follow_the_oracle_conditionals(L, N, ns):
     assert np.array_equal(s2, s[100:250])
     sf = sample_with("ffma", model, flat, ns, seed=seed, sample_offset=off)
     assert (sf == s).all(axis=1).mean() > 0.99
+
+
+def test_batches_beyond_the_workspace_budget_are_evaluated_in_slices():
+    """ops.sample_chunk: with a workspace budget smaller than one call needs, E_loc / log psi are evaluated slice by slice (identical
+    numbers: samples are independent) and the gradient is summed over slices (the same per-sample terms in another summation order)."""
+    N, L, ns = 64, 2, 3000
+    from rnnwavefunctions_b200 import params as P
+    model = ops.make_model(num_layers=L, units=50, n_sites=N)
+    flat = torch.tensor(P.init_flat(P.gru_shapes([50] * L), 3, np.float32), device=dev())
+    s = ops.sample(model, flat, ns, seed=9)
+    w = torch.randn(ns, dtype=torch.float64, device=dev(), generator=torch.Generator(device=dev()).manual_seed(1)) / ns
+    e0, lp0 = ops.tfim_eloc(model, flat, s, np.ones(N), 1.0)
+    ep0, _ = ops.tfim_eloc(model, flat, s, np.ones(N), 1.0, ops.PARITY_SYM)
+    g0 = ops.vmc_grad(model, flat, s, w).clone()
+    l0 = ops.logpsi(model, flat, s).clone()
+    need = ops.workspace_bytes(model, ops.OP_VMC_GRAD, ns)
+    old = os.environ.get("RNNWF_WS_BUDGET_GB")
+    os.environ["RNNWF_WS_BUDGET_GB"] = str(0.1 * need / 2 ** 30)
+    try:
+        ops.release_workspace()
+        assert ops.sample_chunk(model, ops.OP_VMC_GRAD, ns, 0, dev()) < ns
+        assert ops.sample_chunk(model, ops.OP_TFIM_ELOC, ns, ops.PARITY_SYM, dev()) < ns
+        e1, lp1 = ops.tfim_eloc(model, flat, s, np.ones(N), 1.0)
+        ep1, _ = ops.tfim_eloc(model, flat, s, np.ones(N), 1.0, ops.PARITY_SYM)
+        g1 = ops.vmc_grad(model, flat, s, w)
+        l1 = ops.logpsi(model, flat, s)
+    finally:
+        if old is None:
+            os.environ.pop("RNNWF_WS_BUDGET_GB", None)
+        else:
+            os.environ["RNNWF_WS_BUDGET_GB"] = old
+        ops.release_workspace()
+    assert torch.equal(e1, e0) and torch.equal(lp1, lp0) and torch.equal(ep1, ep0) and torch.equal(l1, l0)
+    assert ((g1 - g0).norm() / g0.norm()).item() < 1e-5     # the FP32 accumulators of the weight-gradient reduction group the samples by tile
