@@ -61,6 +61,9 @@
 #ifndef RNNWF_PARTS
 #define RNNWF_PARTS 2     // row threads per sample: 2 (26 units each, 8 row warps at 224 registers) or 3 (18 units each, 12 row warps at 152)
 #endif
+#ifndef RNNWF_SKEW
+#define RNNWF_SKEW 0
+#endif
 #ifndef RNNWF_KPACK
 #define RNNWF_KPACK 1     // 3e: the three split passes packed densely along K (10 MMAs of K = 16 per operand group instead of 12)
 #endif
@@ -380,6 +383,7 @@ struct Ctx {
     float p_laf, accf, compf; // probability head: the site terms are FP32 numbers, summed with Kahan compensation in FP32 -- FP64
                               // instructions in the site loop cost ~150 cycles each on this part (ncu: stall_math on every DADD)
     int nup;
+    bool skew;
     double acc, acc_im;
 #ifdef RNNWF_TC16P_DEBUG
     long long w_ru, w_c, t_ru, t_c;   // cycles: waiting for full_ru / full_c, inside G_ru / G_c
@@ -513,8 +517,13 @@ __device__ __forceinline__ void ru_one(float& r, float& u) {
 }
 __device__ __forceinline__ void ru_pair(float& r0, float& u0, float& r1, float& u1) {
 #if RNNWF_GATES == 0
+#ifdef RNNWF_NOCLAMP   // measurement only: valid when every reset / update pre-activation is known to stay below 30 log 2
+    const float er0 = 1.0f + ex2(r0), eu0 = 1.0f + ex2(u0);
+    const float er1 = 1.0f + ex2(r1), eu1 = 1.0f + ex2(u1);
+#else
     const float er0 = 1.0f + ex2(fminf(r0, 30.f)), eu0 = 1.0f + ex2(fminf(u0, 30.f));
     const float er1 = 1.0f + ex2(fminf(r1, 30.f)), eu1 = 1.0f + ex2(fminf(u1, 30.f));
+#endif
     const float p0 = er0 * eu0, p1 = er1 * eu1;
     const float inv = rcp(p0 * p1);
     const float i0 = inv * p1, i1 = inv * p0;                          // 1/p0, 1/p1
@@ -578,6 +587,13 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     }
     TCP_T(long long t0 = clock64();)
     umma::mbar_wait(&c.bars[kFull], par);
+#if RNNWF_SKEW > 0   // experiment: the part >= 1 warps start a chain RNNWF_SKEW cycles behind the part 0 warps they share a scheduler with
+    if (part != 0 && c.skew) {
+        const long long ts = clock64();
+        while (clock64() - ts < RNNWF_SKEW) {}
+        c.skew = false;
+    }
+#endif
     umma::fence_after_sync();
     TCP_T(long long t1 = clock64(); c.w_ru += t1 - t0;)
     float rr[kUP], uu[kUP], dc[kUP], dq[kUP];
@@ -599,6 +615,18 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
     umma::fence_before_sync();
     umma::mbar_arrive(&c.bars[kAccFree]);              // the accumulators may be overwritten by the next step's MMAs
     TCP_T(long long t2 = clock64(); c.w_c += t2 - t1;)
+#ifdef RNNWF_ABL_NOGATES   // ablation (timing / power only, results are garbage): the tensor pipe alone -- drain, release, hand back
+    if (top) {
+        if (part != 0) umma::mbar_arrive(&c.bars[kZDone]);
+        ++c.zc;
+    }
+    hp[0] += rr[0] + uu[1] + dc[2] + dq[3];
+    umma::fence_before_sync();
+    umma::mbar_arrive(&c.bars[kCDone]);
+    ++c.g;
+    ++c.cda;
+    return;
+#endif
     if (!SAMPLE && part == 0) {
         // the pending head of the last top-layer step.  Three-layer copies: finished in the bottom-layer step, the shortest of the
         // three and the one the top layer's MMAs run under (ncu: the top-layer copy waited 11 % of its time at the commit barrier);
@@ -875,6 +903,9 @@ __device__ __forceinline__ void row_chain_sample(const Args& a, Ctx& c) {
 // where they can (hi x B_hi, hi x B_lo, then lo x B_hi).
 __device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t rH, uint32_t x_1, uint32_t x_2, uint32_t h_1, uint32_t h_2,
                                            bool k16) {
+#ifdef RNNWF_ABL_NOMMA     // ablation (timing / power only, results are garbage): the gate math alone -- no tcgen05.mma, the commit fires at once
+    return;
+#endif
     constexpr uint32_t idAll = (1u << 4) | ((uint32_t)(kNAll >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // F16 x F16 -> F32, M = 128
     constexpr uint32_t idRU = (1u << 4) | ((uint32_t)(kNRU >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t idC = (1u << 4) | ((uint32_t)(kNC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -891,8 +922,12 @@ __device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t
             umma::mma_f16_ts_elect(dX, rX + q * 8, b1 + (uint64_t)(q * 16), idAll, q > 0);
             umma::mma_f16_ts_elect(dX, rX + q * 8, b2 + (uint64_t)(q * 16), idAll, 1);
         }
+#ifndef RNNWF_ABL_SKIPLO   // ablation (timing / power only): without the lo x W_hi products (3 of the 10 MMAs of an operand group)
 #pragma unroll
         for (int q = 3; q < 7; ++q) umma::mma_f16_ts_elect(dX, rX + q * 8, b1 + (uint64_t)((q == 3 ? 6 : 2 * q - 7) * 8), idAll, 1);
+#else
+        umma::mma_f16_ts_elect(dX, rX + 3 * 8, b1 + (uint64_t)(6 * 8), idAll, 1);
+#endif
 #else
         const uint64_t bhi = umma::smem_desc(x_1, 128, kKC * 128), blo = umma::smem_desc(x_2, 128, kKC * 128);
 #pragma unroll
@@ -915,8 +950,12 @@ __device__ __forceinline__ void issue_step(uint32_t tbase, uint32_t rX, uint32_t
             umma::mma_f16_ts_elect(dH, rH + q * 8, b1 + (uint64_t)(q * 16), idAll, 1);
             umma::mma_f16_ts_elect(dH, rH + q * 8, b2 + (uint64_t)(q * 16), idAll, 1);
         }
+#ifndef RNNWF_ABL_SKIPLO
 #pragma unroll
         for (int q = 3; q < 7; ++q) umma::mma_f16_ts_elect(dH, rH + q * 8, b1 + (uint64_t)((q == 3 ? 6 : 2 * q - 7) * 8), idAll, 1);
+#else
+        umma::mma_f16_ts_elect(dH, rH + 3 * 8, b1 + (uint64_t)(6 * 8), idAll, 1);
+#endif
 #else
         const uint64_t bhi = umma::smem_desc(h_1, 128, kKC * 128), blo = umma::smem_desc(h_2, 128, kKC * 128);
         umma::mma_f16_ts_elect(dH, rH, bhi, idRU, 1);
@@ -977,7 +1016,7 @@ __device__ __forceinline__ uint32_t work_loop(const Args& a, const float* tab, f
             if constexpr (ROW) {
                 Ctx c;
                 c.tab = tab; c.zsm = zsm; c.bars = bars; c.lane_addr = lane_addr; c.rowi = rowi; c.m = m; c.part = part; c.live = live;
-                c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.zc = ztop; c.acc = acc; c.acc_im = acc_im;
+                c.rowbase = rowbase; c.s = s; c.t = tt; c.g = gstep; c.cda = cdp; c.zc = ztop; c.skew = true; c.acc = acc; c.acc_im = acc_im;
                 c.pz = make_float4(0.f, 0.f, 0.f, 0.f); c.psg = 0; c.pn = -1; c.pph = 0; c.pbuf = 0; c.nup = 0; c.p_la = 0.0; c.p_ph = 0.0; c.p_laf = 0.f; c.accf = 0.f; c.compf = 0.f;
                 TCP_T(c.w_ru = c.w_c = c.t_ru = c.t_c = 0; long long ch0 = clock64();)
                 if constexpr (SAMPLE) row_chain_sample<CPLX>(a, c);
