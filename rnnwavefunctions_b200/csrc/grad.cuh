@@ -509,11 +509,16 @@ __global__ void __launch_bounds__(kWgfThreads) wgrad_fast_kernel(WgradArgs<float
 // previous block's MMAs into (hi, lo) core-matrix images in shared memory, one thread issues 3 MMAs per 8 samples, and the global
 // loads of the next block are in flight while the tensor pipe works.  (The warp-level mma.sync m16n8k8 TF32 path was measured first:
 // 94 ms against the 74 ms of the FFMA kernel at cfg2 -- on sm_100a it runs at ~4x the FFMA rate, which three passes eat.)
+// Sub-blocks: the samples of a (tile, site) block are taken in nsub slices of Ms (68 rows: 36 + 32).  The images of a slice are
+// half as large (110 instead of 198 KB at cfg2), so TWO CTAs share an SM: one splits / stores its operands or waits for its loads
+// while the tensor pipe works for the other, and twice as many loads are in flight (the one-CTA version was bound by the latency of
+// its one-block-deep register prefetch: ncu long_scoreboard 4.3 stalls per issue, tensor pipe 22 %, 1.87 TB/s of DRAM reads).
 namespace wgtc {
-constexpr int kThreads = 256, kMaxItems = 24;
+constexpr int kThreads = 256, kMaxItems = 16;
 
 struct Geo {
     int Rp8, Cp8, Np, Kp, M4p, items, nit;      // padded A / B rows, MMA N, padded samples, float4 columns (multiple of 4)
+    int Ms, nsub;                               // samples per slice (multiple of 4), slices per block
     size_t img_floats, smem;
 };
 inline Geo make_geo(int R, int cols, int M) {
@@ -521,8 +526,10 @@ inline Geo make_geo(int R, int cols, int M) {
     q.Rp8 = (R + 7) / 8 * 8;
     q.Cp8 = (cols + 7) / 8 * 8;
     q.Np = (cols + 15) / 16 * 16;
-    q.Kp = (M + 7) / 8 * 8;
-    q.M4p = (M / 4 + 3) / 4 * 4;
+    q.nsub = M > 40 ? 2 : 1;
+    q.Ms = ((M + q.nsub - 1) / q.nsub + 3) / 4 * 4;
+    q.Kp = (q.Ms + 7) / 8 * 8;
+    q.M4p = (q.Ms / 4 + 3) / 4 * 4;
     q.items = (q.Rp8 + q.Cp8) * q.M4p;
     q.nit = (q.items + kThreads - 1) / kThreads;
     q.img_floats = (size_t)(128 + q.Np + 8) * q.Kp;                 // A image | B image (+ one row group of slack)
@@ -532,7 +539,7 @@ inline Geo make_geo(int R, int cols, int M) {
 inline bool supported(int R, int cols, int M) {
     if (R > 128 || cols > 256 || M % 4 != 0) return false;
     const Geo q = make_geo(R, cols, M);
-    return q.nit <= kMaxItems && q.smem <= (size_t)kSmemLimit;
+    return q.nit <= kMaxItems && q.smem <= (size_t)kSmemLimit && q.img_floats / 4 < 4096;   // image offsets are 12-bit fields of the item descriptors
 }
 
 // what a thread moves per block is fixed for the whole launch: item -> (source kind, element offset relative to the block's base,
@@ -541,21 +548,22 @@ inline bool supported(int R, int cols, int M) {
 // no_instruction stalls)
 enum { kSkip = 0, kStash = 1, kGate = 2, kOneHot = 3 };
 
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, Geo q, double* __restrict__ partial, int Rp, int Cp) {
+__global__ void __launch_bounds__(kThreads, 2) wgrad_kernel(WgradArgs<float> a, Geo q, double* __restrict__ partial, int Rp, int Cp) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* img_hi = reinterpret_cast<float*>(smem);
     float* img_lo = img_hi + q.img_floats;
     uint64_t* bar = reinterpret_cast<uint64_t*>(img_lo + q.img_floats);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int R = a.rows0 + a.rows1 + 1, KC = q.Kp / 4, M = a.M;
+    const int R = a.rows0 + a.rows1 + 1, KC = q.Kp / 4, M = a.M, Ms = q.Ms, nsub = q.nsub;
     const int ks = blockIdx.x;
-    const int64_t b0 = a.nblk * ks / a.ksplit, b1 = a.nblk * (ks + 1) / a.ksplit;
+    const int64_t nvb = a.nblk * nsub;                                                  // (block, slice) pairs
+    const int64_t b0 = nvb * ks / a.ksplit, b1 = nvb * (ks + 1) / a.ksplit;
     double* out = partial + (size_t)ks * Rp * Cp;
     for (int i = tid; i < Rp * Cp; i += blockDim.x) out[i] = 0.0;
     for (size_t i = tid; i < 2 * q.img_floats; i += blockDim.x) img_hi[i] = 0.f;       // padding rows / samples stay zero
     __syncthreads();
-    for (int i = tid; i < M; i += blockDim.x) {                                        // the constant-1 row (biases) never changes
+    for (int i = tid; i < Ms; i += blockDim.x) {                                       // the constant-1 row (biases) never changes
         const int irow = R - 1;
         img_hi[(size_t)(irow >> 3) * (KC * 32) + (size_t)(i >> 2) * 32 + (irow & 7) * 4 + (i & 3)] = 1.0f;
     }
@@ -571,15 +579,17 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
     // item -> (row, float4 column): 8 consecutive lanes take the 8 rows of a core-matrix row group (one conflict-free 128-byte store),
     // the 4 lane groups of a warp take 4 consecutive float4 columns (64 contiguous bytes of every row in global memory)
     const int RG = (q.Rp8 + q.Cp8) / 8;
-    int goff[kMaxItems], dsc[kMaxItems];      // element offset from the block's base; kind | zero-at-site-0 flag << 2 | one-hot row << 3 | image offset (float4) << 8
+    // one register per item (two CTAs share an SM: 128 registers per thread; with separate offset / descriptor arrays ptxas spilled
+    // them and every prefetch waited for local-memory loads): kind [0, 2) | zero-at-site-0 [2] | beyond the tile in the last slice [3] |
+    // one-hot row [4] | image offset in float4 [5, 17) | signed element offset from the block's base [17, 32)
+    int dsc[kMaxItems];
 #pragma unroll
     for (int it = 0; it < kMaxItems; ++it) {
         const int i = tid + it * kThreads;
-        goff[it] = 0;
         dsc[it] = kSkip;
         if (it < q.nit && i < q.items) {
             const int b32 = i >> 5, row = (b32 % RG) * 8 + (i & 7), m4 = ((b32 / RG) * 4 + ((i >> 3) & 3)) * 4;
-            if (m4 < M) {
+            if (m4 < Ms) {
                 const int irow = row < q.Rp8 ? row : 128 + (row - q.Rp8);
                 const int o4 = (int)(((size_t)(irow >> 3) * (KC * 32) + (size_t)(m4 >> 2) * 32 + (irow & 7) * 4) >> 2);
                 int kind = kSkip, flags = 0, off = 0;
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
                     const int r = row;
                     if (r < a.rows0) {
                         if (a.xmode == 1) { kind = kStash; off = (a.lx * a.H + r) * M + m4; }
-                        else { kind = kOneHot; flags = r << 3; off = m4 - M; }                 // sigT of block blk - 1
+                        else { kind = kOneHot; flags = r << 4; off = m4 - M; }                 // sigT of block blk - 1
                     } else if (r < a.rows0 + a.rows1) {
                         kind = kStash;
                         off = ((a.lh - a.hshift * a.L) * a.H + (r - a.rows0)) * M + m4;        // hstore of block blk - hshift
@@ -597,27 +607,30 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
                     kind = kGate;
                     off = (row - q.Rp8) * M + m4;
                 }
-                goff[it] = off;
-                dsc[it] = kind | flags | (o4 << 8);
+                dsc[it] = kind | flags | ((nsub - 1) * Ms + m4 >= M ? 8 : 0) | (o4 << 5) | (int)((uint32_t)off << 17);
             }
         }
     }
     const int64_t hspan = (int64_t)a.L * a.H * M, gspan = (int64_t)a.cols * M;
     float4 pre[kMaxItems];
-    auto prefetch = [&](int64_t blk) {
-        const bool first_site = blk % a.N == 0;
-        const float* hb = a.hstore + blk * hspan;
-        const float* gb = a.B + blk * gspan;
-        const uint8_t* sb = a.sigT + blk * M;
+    auto prefetch = [&](int64_t vb) {
+        const int64_t blk = vb / nsub;
+        const int sub = (int)(vb - blk * nsub), m0 = sub * Ms;
+        const bool first_site = blk % a.N == 0, last = sub == nsub - 1;
+        const float* hb = a.hstore + blk * hspan + m0;
+        const float* gb = a.B + blk * gspan + m0;
+        const uint8_t* sb = a.sigT + blk * M + m0;
 #pragma unroll
         for (int it = 0; it < kMaxItems; ++it) {
             const int kind = dsc[it] & 3;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kind == kGate) v = *reinterpret_cast<const float4*>(gb + goff[it]);
-            else if (kind == kStash) { if (!((dsc[it] & 4) && first_site)) v = *reinterpret_cast<const float4*>(hb + goff[it]); }
+            const int goff = dsc[it] >> 17;
+            if (last && (dsc[it] & 8)) { pre[it] = v; continue; }
+            if (kind == kGate) v = *reinterpret_cast<const float4*>(gb + goff);
+            else if (kind == kStash) { if (!((dsc[it] & 4) && first_site)) v = *reinterpret_cast<const float4*>(hb + goff); }
             else if (kind == kOneHot && !first_site) {
-                const uint32_t sg = *reinterpret_cast<const uint32_t*>(sb + goff[it]);
-                const int r = (dsc[it] >> 3) & 31;
+                const uint32_t sg = *reinterpret_cast<const uint32_t*>(sb + goff);
+                const int r = (dsc[it] >> 4) & 1;
                 v.x = (int)(sg & 0xff) == r ? 1.f : 0.f;
                 v.y = (int)((sg >> 8) & 0xff) == r ? 1.f : 0.f;
                 v.z = (int)((sg >> 16) & 0xff) == r ? 1.f : 0.f;
@@ -634,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
 #pragma unroll
         for (int it = 0; it < kMaxItems; ++it) {
             if ((dsc[it] & 3) != kSkip) {
-                const size_t o = (size_t)(dsc[it] >> 8) << 2;
+                const size_t o = (size_t)((dsc[it] >> 5) & 0xfff) << 2;
                 float4 hi, lo;
                 umma::split_tf32_fast(pre[it].x, hi.x, lo.x);      // integer rounding: cvt.rna.tf32 issues at a quarter of the ALU rate
                 umma::split_tf32_fast(pre[it].y, hi.y, lo.y);
@@ -660,7 +673,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<float> a, 
         }
         ++commits;
         if (blk + 1 < b1) prefetch(blk + 1);                             // in flight while the tensor pipe works
-        if (++pending == kWgFlush || blk + 1 == b1) {
+        if (++pending == kWgFlush * nsub || blk + 1 == b1) {      // the same number of samples per FP32 accumulator as with whole blocks
             umma::mbar_wait(bar, (commits - 1) & 1);
             umma::fence_after_sync();
             const int row = 32 * (warp & 3) + lane, half = q.Np / 2 / 8 * 8;     // warps 0-3: columns [0, half), warps 4-7: the rest
@@ -879,7 +892,8 @@ static int launch_wgrad(const GruLayout& g, const GradWs<T>& w, int M, int64_t n
     a.ksplit = w.ksplit;
     bool fast = false;
     if constexpr (std::is_same<T, float>::value) {
-        if (wgtc::supported(R, a.cols, M) && !getenv("RNNWF_WGRAD_FFMA")) {   // layers and the head alike
+        const bool offs_fit = (int64_t)g.L * g.H * M < 16384 && (int64_t)a.cols * M < 16384;   // 15-bit signed element offsets in the item descriptors
+        if (wgtc::supported(R, a.cols, M) && offs_fit && !getenv("RNNWF_WGRAD_FFMA")) {   // layers and the head alike
             fast = true;
             const wgtc::Geo q = wgtc::make_geo(R, a.cols, M);
             auto k = wgtc::wgrad_kernel;
