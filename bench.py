@@ -458,7 +458,9 @@ def run_b200_arm(args):
                         note="achieved counts ALGORITHMIC flops (F per GRU-stack evaluation); FP32-grade accuracy costs three split-operand products "
                              "(hi*hi + hi*lo + lo*hi); packed densely along K they take 10 MMAs of K = 16 per operand group (152 of 160 K slots "
                              "used) over N = 160 (150 used): the tensor pipe executes ~3.6x the algorithmic flops.  The board runs this kernel at "
-                             "its power cap (see clocks), so executed tensor work is what sets the time")
+                             "its power cap (see clocks).  Ablation builds on one box (profiles/r2/ab_power_ablation.log): the gate math alone "
+                             "takes the same cycle count as the whole kernel (the MMAs are hidden in cycles), the tensor pipe alone needs 64 % "
+                             "of it, and the cap costs ~10 % of the clock -- the tensor pipe's energy, i.e. the executed MMA count, sets the time")
 
     # ---- end to end through the reference-facing host API (host buffers, copies inside the timed region) ----
     e2e = None
