@@ -311,6 +311,24 @@ static bool sampler_tc(const GruLayout& g) {
     if (e && strcmp(e, "ffma") == 0) return false;
     return tc16p::supported_padded(g);
 }
+static bool logpsi_tc(const GruLayout& g) {      // RNNWF_LOGPSI=ffma keeps the CUDA-core forward kernel (A/B measurements, cross-checks)
+    const char* e = getenv("RNNWF_LOGPSI");
+    if (e && strcmp(e, "ffma") == 0) return false;
+    return tc16p::supported_padded(g);
+}
+struct LogpsiTcWs { uint8_t* sigT; double *lp_re, *lp_im; unsigned char* img; int* counter; int tiles_s, tiles; };
+static LogpsiTcWs carve_logpsi_tc(Ws& ws, const GruLayout& g, int64_t ns, int ndir, bool cplx) {
+    LogpsiTcWs w;
+    w.tiles_s = (int)cdiv(ns, tc16p::kRows);
+    w.tiles = w.tiles_s * ndir;
+    const size_t rows = (size_t)w.tiles * tc16p::kRows;
+    w.sigT = ws.take<uint8_t>(rows * g.N);
+    w.lp_re = ws.take<double>(rows);
+    w.lp_im = ws.take<double>(cplx ? rows : 0);
+    w.img = ws.take<unsigned char>(tc16_img_bytes(g));
+    w.counter = ws.take<int>(4);
+    return w;
+}
 struct SampleTcWs { uint8_t* sampT; unsigned char* img; int* counter; int tiles128; };
 static SampleTcWs carve_sample_tc(Ws& ws, const GruLayout& g, int64_t ns) {
     SampleTcWs w;
@@ -342,7 +360,14 @@ template <typename T> size_t gru_workspace_bytes_t(const rnnwf_model& m, int op,
                 ws.used = std::max(ws.used, w2.used);
                 break;
             }
-        case RNNWF_OP_LOGPSI: carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns); break;
+        case RNNWF_OP_LOGPSI:
+            carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns);
+            if (std::is_same<T, float>::value && tc16p::supported_padded(g)) {   // whichever kernel RNNWF_LOGPSI picks at run time fits
+                Ws w2(nullptr, 0);
+                carve_logpsi_tc(w2, g, ns, ndir, cplx);
+                ws.used = std::max(ws.used, w2.used);
+            }
+            break;
         case RNNWF_OP_TFIM_ELOC:
             carve_gru<T>(ws, carve_layout<T>(g), c, tiles, true, g.N, cplx, ns);
 #ifdef RNNWF_LEGACY
@@ -401,11 +426,23 @@ template <typename T>
 int gru_logpsi_t(const rnnwf_model& m, const void* params, const uint8_t* samples, int64_t ns, int flags, double* out, void* wsp,
                  size_t wsb, cudaStream_t s) {
     const GruLayout g = make_gru_layout(m);
-    const GruLaunch c = choose_gru_launch<T>(g, ns, (flags & RNNWF_PARITY_SYM) ? 2 : 1);
-    RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
     const bool cplx = m.head == RNNWF_HEAD_COMPLEX;
     const int parity = (flags & RNNWF_PARITY_SYM) ? 1 : 0;
     RNNWF_CHECK(!(cplx && parity), -2, "parity symmetry is only defined for the probability head");
+    if constexpr (std::is_same<T, float>::value) {
+        if (logpsi_tc(g)) {      // the tensor-core base pass without its stash
+            Ws ws(wsp, wsb);
+            LogpsiTcWs w = carve_logpsi_tc(ws, g, ns, parity ? 2 : 1, cplx);
+            RNNWF_CHECK(ws.ok(), -4, "workspace too small: need %zu have %zu", ws.used, wsb);
+            prof_count(); sig_transpose_kernel<<<grid_for((int64_t)w.tiles * g.N * tc16p::kRows), 256, 0, s>>>(samples, w.sigT, ns, g.N, tc16p::kRows, w.tiles_s, parity ? 2 : 1);
+            if (int e = tc16p::launch_logpsi(g, w.tiles, (const float*)params, w.img, w.sigT, w.lp_re, w.lp_im, w.counter, s)) return e;
+            prof_count(); gather_logpsi_kernel<<<grid_for(ns), 256, 0, s>>>(w.lp_re, w.lp_im, ns, tc16p::kRows, w.tiles_s, parity, cplx, out);
+            RNNWF_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
+    const GruLaunch c = choose_gru_launch<T>(g, ns, parity ? 2 : 1);
+    RNNWF_CHECK(c.RT > 0, -3, "no launch configuration fits (units=%d layers=%d)", m.units, m.num_layers);
     const int tiles_s = (int)cdiv(ns, c.M), ndir = parity ? 2 : 1, tiles = tiles_s * ndir;
     Ws ws(wsp, wsb);
     GruWs<T> w = carve_gru<T>(ws, g, c, tiles, false, 0, cplx, ns);

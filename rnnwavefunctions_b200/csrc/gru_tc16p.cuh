@@ -442,10 +442,13 @@ template <bool BASE, bool CPLX> __device__ __forceinline__ void finish_head(cons
     }
     const size_t o_ = (c.rowbase + pn) * a.Mold + c.m;
     if (BASE) {
-        a.la_sel[o_] = ls;
-        a.la_oth[o_] = lo;
+        if (a.la_sel != nullptr) {             // log psi alone (rnnwf_logpsi) keeps no per-site terms
+            a.la_sel[o_] = ls;
+            a.la_oth[o_] = lo;
+            if (CPLX) { a.ph_sel[o_] = ps; a.ph_oth[o_] = po; }
+        }
         c.acc += ls;
-        if (CPLX) { a.ph_sel[o_] = ps; a.ph_oth[o_] = po; c.acc_im += ps; }
+        if (CPLX) c.acc_im += ps;
     } else {
         c.acc += ls - c.p_la;
         if (CPLX) c.acc_im += ps - c.p_ph;
@@ -475,11 +478,13 @@ template <bool BASE, bool LATE = false> __device__ __forceinline__ void finish_h
     const float ls = dsel > 30.f ? -dsel : -log1pf(expf(dsel));
     float term = ls;
     if (BASE) {
-        const float lo = -dsel > 30.f ? dsel : -log1pf(expf(-dsel));
-        const size_t o_ = (c.rowbase + pn) * a.Mold + c.m;
-        a.la_sel[o_] = (double)ls;
-        a.la_oth[o_] = (double)lo;
-        a.la_self[o_] = ls;
+        if (a.la_sel != nullptr) {             // log psi alone (rnnwf_logpsi) keeps no per-site terms
+            const float lo = -dsel > 30.f ? dsel : -log1pf(expf(-dsel));
+            const size_t o_ = (c.rowbase + pn) * a.Mold + c.m;
+            a.la_sel[o_] = (double)ls;
+            a.la_oth[o_] = (double)lo;
+            a.la_self[o_] = ls;
+        }
     } else {
         term = ls - c.p_laf;
     }
@@ -715,7 +720,7 @@ __device__ __forceinline__ void row_step(const Args& a, Ctx& c, int n, int l_dyn
                     y1 = fmaf(h1, tab[132 + 2 * jl + 3], y1);
                 }
             }
-            if (BASE && !SAMPLE && c.live) {
+            if (BASE && !SAMPLE && c.live && a.hstore != nullptr) {
                 hst[(size_t)jl * Mold] = h0;
                 hst[(size_t)(jl + 1) * Mold] = h1;
             }
@@ -1222,6 +1227,17 @@ static int launch_eloc(const GruLayout& greal, int Mold, int tiles, const float*
     a.gstore = gstore;
     prof_count(); pack_kernel<<<148, 256, 0, s>>>(greal, a.t, params, img);
     return launch_chains<false>(a, sms, flips, s);
+}
+
+// log psi alone: the base pass without the stash of restart states and per-site terms (rnnwf_logpsi)
+static int launch_logpsi(const GruLayout& greal, int tiles128, const float* params, unsigned char* img, const uint8_t* sigT, double* lp_re,
+                         double* lp_im, int* counter, cudaStream_t s) {
+    int sms;
+    const GruLayout g = padded_layout(greal);
+    Args a = make_args(g, kRows, tiles128, img, sigT, nullptr, nullptr, nullptr, nullptr, lp_re, nullptr, counter, sms);
+    a.lp_im = lp_im;
+    prof_count(); pack_kernel<<<148, 256, 0, s>>>(greal, a.t, params, img);
+    return g.nheads == 2 ? launch_chains<true>(a, sms, false, s) : launch_chains<false>(a, sms, false, s);
 }
 
 // autoregressive sampler (probability head, or the cRNN's amplitude head with the U(1) mask): 128-row tiles, one persistent CTA each

@@ -279,3 +279,24 @@ def test_batches_beyond_the_workspace_budget_are_evaluated_in_slices():
         ops.release_workspace()
     assert torch.equal(e1, e0) and torch.equal(lp1, lp0) and torch.equal(ep1, ep0) and torch.equal(l1, l0)
     assert ((g1 - g0).norm() / g0.norm()).item() < 1e-5     # the FP32 accumulators of the weight-gradient reduction group the samples by tile
+
+
+@pytest.mark.parametrize("L,N,ns,parity", [(1, 20, 150, False), (3, 37, 300, True), (2, 64, 200, False), (3, 130, 260, False)])
+def test_log_probability_on_the_tensor_core_base_pass(L, N, ns, parity):
+    """rnnwf_logpsi for the stacks the tcgen05 kernel covers = its base pass without the stash (1DTFIM/RNNwavefunction.py:76-118,
+    RNNwavefunction_paritysym.py:125-145): against the oracle (1e-5) and the CUDA-core forward kernel (RNNWF_LOGPSI=ffma)."""
+    units = [50] * L
+    p = O.randomize_biases(O.init_gru_params(units, seed=20 + L, dtype=np.float32, scale=2.0), seed=L + 2)
+    model = ops.make_model(num_layers=L, units=50, n_sites=N)
+    flat = torch.tensor(O.flatten(p), device=dev())
+    s = O.sample(p, ns, N, seed=4)
+    flags = ops.PARITY_SYM if parity else 0
+    got = ops.logpsi(model, flat, u8(s), flags).cpu().numpy()
+    os.environ["RNNWF_LOGPSI"] = "ffma"
+    try:
+        ff = ops.logpsi(model, flat, u8(s), flags).cpu().numpy()
+    finally:
+        os.environ.pop("RNNWF_LOGPSI", None)
+    ref = O.log_probability_parity(p, s) if parity else O.log_probability(p, s)
+    np.testing.assert_allclose(got, ref, rtol=1e-5)
+    np.testing.assert_allclose(got, ff, rtol=1e-5)
