@@ -13,6 +13,7 @@
 #include "gru_kernels.cuh"
 #include "host_util.cuh"
 #include "umma.cuh"
+#include "wgrad_f64mma.cuh"
 
 namespace rnnwf {
 
@@ -699,121 +700,33 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_kernel(WgradArgs<float> a, 
 }
 }  // namespace wgtc
 
-// float64 path of the same reduction on the FP64 tensor instruction (mma.sync.m8n8k4.f64, DMMA) -- the 2-D apps of the reference
-// compute in float64 (2DTFIM_1DRNN/RNNwavefunction.py:26-38), and the thread-tile kernel above spent 85 ms of cfg3's 446 ms step here
-// (1.4 TFLOP/s: 8 LDS.128 per 16 DFMA, every operand re-read rtiles * ctiles times).  C[r][c] = sum_(blk, m) A[r][m] B[c][m] is a GEMM with
-// K = the samples of the (tile, site) blocks, and both operands lie K-contiguous in HBM ([row][M]), which is what the DMMA fragments
-// want: lane (g = lane / 4, q = lane % 4) holds A[8 mt + g][k0 + q] and B[8 nt + g][k0 + q], and C[8 mt + g][8 nt + 2 q + {0, 1}].
-// One CTA owns a [104 x 104] output tile (13 x 13 fragments over a 4 x 4 grid of warps, at most 4 x 4 fragments = 32 accumulators per
-// thread, FP64, kept in registers for the whole launch: fixed summation order, no atomics) and a share of the blocks; the operands
-// go through a 4-stage cp.async ring of K slices of 16 samples (row stride 20 doubles: conflict-free LDS.64 for the fragment pattern).
-namespace wgdm {
-constexpr int kThreads = 512, kT = 104, kKS = 16, kMS = 20, kStages = 4;
-constexpr int kStageDoubles = 2 * kT * kMS;
-constexpr size_t kSmem = (size_t)kStages * kStageDoubles * sizeof(double);     // 133 KB
 
-__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-__global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(WgradArgs<double> a, int ct, int ksplit, double* __restrict__ partial, int Rp, int Cp) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double* buf = reinterpret_cast<double*>(smem);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g8 = lane >> 2, q4 = lane & 3;
-    const int M = a.M, R = a.rows0 + a.rows1 + 1;
-    const int tile = blockIdx.x, ks = blockIdx.y;
-    const int r0 = (tile / ct) * kT, c0 = (tile % ct) * kT;
-    const int64_t b0 = a.nblk * ks / ksplit, b1 = a.nblk * (ks + 1) / ksplit;
-    const int nsl = (M + kKS - 1) / kKS;
-    const int64_t T = (b1 - b0) * nsl;
-    // fragments of this warp: 13 = 4 + 3 + 3 + 3 in both directions
-    const int wm = warp >> 2, wn = warp & 3;
-    const int mt0 = wm == 0 ? 0 : 1 + 3 * wm, nm = wm == 0 ? 4 : 3;
-    const int nt0 = wn == 0 ? 0 : 1 + 3 * wn, nn = wn == 0 ? 4 : 3;
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    auto issue = [&](int64_t t) {      // K slice t of this CTA -> stage t % kStages
-        const int64_t blk = b0 + t / nsl;
-        const int k0 = (int)(t % nsl) * kKS, n = (int)(blk % a.N);
-        double* A = buf + (size_t)(t % kStages) * kStageDoubles;
-        double* B = A + kT * kMS;
-        for (int i = tid; i < 2 * kT * (kKS / 2); i += kThreads) {
-            const int row = i / (kKS / 2), k = k0 + 2 * (i % (kKS / 2));
-            double* dst = (row < kT ? A + row * kMS : B + (row - kT) * kMS) + (k - k0);
-            const double* src = nullptr;
-            bool special = false;
-            if (row < kT) {
-                const int r = r0 + row;
-                if (r < a.rows0) {
-                    if (a.xmode == 1) src = a.hstore + ((blk * a.L + a.lx) * a.H + r) * M + k;
-                    else special = true;                                   // one-hot input row
-                } else if (r < a.rows0 + a.rows1) {
-                    if (!(a.hshift && n == 0)) src = a.hstore + (((blk - a.hshift) * a.L + a.lh) * a.H + (r - a.rows0)) * M + k;
-                } else if (r == R - 1) {
-                    special = true;                                        // the constant-1 row (biases)
-                }
-                if (special) {
-                    double v0 = 0.0, v1 = 0.0;
-                    if (r == R - 1) { v0 = k < M ? 1.0 : 0.0; v1 = k + 1 < M ? 1.0 : 0.0; }
-                    else if (n > 0) {
-                        if (k < M) v0 = a.sigT[(blk - 1) * M + k] == r ? 1.0 : 0.0;
-                        if (k + 1 < M) v1 = a.sigT[(blk - 1) * M + k + 1] == r ? 1.0 : 0.0;
-                    }
-                    *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-                    continue;
-                }
-            } else {
-                const int cc = c0 + row - kT;
-                if (cc < a.cols) src = a.B + (blk * a.cols + cc) * M + k;
+// operands of the GRU reduction for wgdm::wgrad_kernel (wgrad_f64mma.cuh)
+struct WgdmGruSrc {
+    WgradArgs<double> a;
+    int M, R, C;
+    int64_t nblk;
+    __device__ __forceinline__ const double* a_src(int64_t blk, int r, int k, bool& special, double& v0, double& v1) const {
+        const int n = (int)(blk % a.N);
+        if (r < a.rows0) {
+            if (a.xmode == 1) return a.hstore + ((blk * a.L + a.lx) * a.H + r) * M + k;
+            special = true;                                                // one-hot input row: sigma of the site before
+            if (n > 0) {
+                v0 = a.sigT[(blk - 1) * M + k] == r ? 1.0 : 0.0;
+                v1 = a.sigT[(blk - 1) * M + k + 1] == r ? 1.0 : 0.0;
             }
-            if (src != nullptr && k < M) cp_async16(dst, src);            // M is even: a 16-byte piece never straddles the tile
-            else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+            return nullptr;
         }
-    };
-
-    for (int t = 0; t < kStages - 1; ++t) {
-        if (t < T) issue(t);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (r < a.rows0 + a.rows1) {
+            if (a.hshift && n == 0) return nullptr;
+            return a.hstore + (((blk - a.hshift) * a.L + a.lh) * a.H + (r - a.rows0)) * M + k;
+        }
+        special = true;                                                    // the constant-1 row (biases)
+        v0 = v1 = 1.0;
+        return nullptr;
     }
-    for (int64_t t = 0; t < T; ++t) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
-        __syncthreads();                                                  // slice t has landed; everybody is done with slice t - 1
-        if (t + kStages - 1 < T) issue(t + kStages - 1);
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        const double* A = buf + (size_t)(t % kStages) * kStageDoubles + (size_t)(8 * mt0 + g8) * kMS + q4;
-        const double* B = buf + (size_t)(t % kStages) * kStageDoubles + (size_t)(kT + 8 * nt0 + g8) * kMS + q4;
-#pragma unroll
-        for (int kk = 0; kk < kKS; kk += 4) {
-            double af[4], bf[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = i < nm ? A[i * 8 * kMS + kk] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = j < nn ? B[j * 8 * kMS + kk] : 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (i < nm && j < nn) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i < nm && j < nn) {
-                const int r = r0 + 8 * (mt0 + i) + g8, c = c0 + 8 * (nt0 + j) + 2 * q4;
-                if (r < Rp) {
-                    if (c < Cp) partial[((size_t)ks * Rp + r) * Cp + c] = acc[i][j][0];
-                    if (c + 1 < Cp) partial[((size_t)ks * Rp + r) * Cp + c + 1] = acc[i][j][1];
-                }
-            }
-        }
-}
-}  // namespace wgdm
+    __device__ __forceinline__ const double* b_src(int64_t blk, int c, int k) const { return a.B + (blk * a.cols + c) * M + k; }
+};
 
 // sum the split-K partials (fixed order) and scatter into the flat gradient.
 //   layer mode : rows [x (d) | h (H) | ones], cols [da_r (H) | da_u (H) | da_c (H) | dq (H)]
@@ -1035,10 +948,12 @@ static int launch_wgrad(const GruLayout& g, const GradWs<T>& w, int M, int64_t n
             const int Rp = a.rtiles * kWgTile, Cp = a.ctiles * kWgTile;
             const int rt = (int)cdiv(R, wgdm::kT), ct = (int)cdiv(a.cols, wgdm::kT);
             const int64_t slots = ((int64_t)w.ksplit * w.Rp * w.Cp) / ((int64_t)Rp * Cp);      // what the partial buffer holds
-            ksplit_used = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(slots, nblk), std::max(1, 148 / (rt * ct))));
-            auto k = wgdm::wgrad_kernel;
+            ksplit_used = wgdm::choose_ksplit(R, a.cols, nblk, slots);
+            WgdmGruSrc src;
+            src.a = a; src.M = M; src.R = R; src.C = a.cols; src.nblk = nblk;
+            auto k = wgdm::wgrad_kernel<WgdmGruSrc>;
             if (int e = set_smem(k, (int)wgdm::kSmem)) return e;
-            prof_count(); k<<<dim3(rt * ct, ksplit_used), wgdm::kThreads, wgdm::kSmem, s>>>(a, ct, ksplit_used, w.partial, Rp, Cp);
+            prof_count(); k<<<dim3(rt * ct, ksplit_used), wgdm::kThreads, wgdm::kSmem, s>>>(src, ct, ksplit_used, w.partial, Rp, Cp);
             RNNWF_CUDA(cudaGetLastError());
             fast = true;
         }

@@ -18,6 +18,7 @@
 #include "gru_engine.cuh"
 #include "host_util.cuh"
 #include "api_internal.h"
+#include "wgrad_f64mma.cuh"
 
 namespace rnnwf {
 
@@ -530,6 +531,43 @@ __global__ void __launch_bounds__(256) md_wgrad_kernel(MdLayout g, MdWgArgs<T> a
         for (int j = 0; j < 2; ++j) partial[((size_t)ks * Rp + r0 + tr * 2 + i) * Cp + c0 + tc * 2 + j] = acc[i][j];
 }
 
+// operands of the 2-D RNN reduction for wgdm::wgrad_kernel (wgrad_f64mma.cuh; float64 models)
+struct WgdmMdSrc {
+    MdLayout g;
+    MdWgArgs<double> a;
+    int M, R, C;
+    int64_t nblk;
+    __device__ __forceinline__ const double* a_src(int64_t blk, int r, int k, bool& special, double& v0, double& v1) const {
+        const int H = g.H, N = g.N;
+        if (a.head) {
+            if (r < H) return a.hgrid + ((size_t)blk * H + r) * M + k;
+            special = true;
+            v0 = v1 = 1.0;
+            return nullptr;
+        }
+        const int p = (int)(blk % N);
+        const int64_t st = blk / N;
+        int x, y, pl, pu, pd;
+        md_decode(g, p, x, y, pl, pu, pd);
+        if (r < H) return pl >= 0 ? a.hgrid + (((size_t)st * N + pl) * H + r) * M + k : nullptr;
+        if (r < 2 * H) return pu >= 0 ? a.hgrid + (((size_t)st * N + pu) * H + (r - H)) * M + k : nullptr;
+        special = true;
+        if (r < 2 * H + 4) {                                              // one-hot of the left / upper spin
+            const int which = (r - 2 * H) >> 1, bit = (r - 2 * H) & 1, q = which ? pu : pl;
+            const int64_t rowid = st * M + k;
+            if (q >= 0) {
+                const int site = md_site(g, q);
+                if (rowid < a.ns) v0 = a.samples[rowid * N + site] == bit ? 1.0 : 0.0;
+                if (rowid + 1 < a.ns) v1 = a.samples[(rowid + 1) * N + site] == bit ? 1.0 : 0.0;
+            }
+        } else {
+            v0 = v1 = 1.0;                                                // bias row
+        }
+        return nullptr;
+    }
+    __device__ __forceinline__ const double* b_src(int64_t blk, int c, int k) const { return a.B + ((size_t)blk * a.C + c) * M + k; }
+};
+
 __global__ void md_wgrad_scatter_kernel(MdLayout g, const double* __restrict__ partial, int ksplit, int Rp, int Cp, int head, int R,
                                         int C, double* __restrict__ grad) {
     const int H = g.H;
@@ -770,11 +808,29 @@ static int md_launch_wgrad(const MdLayout& g, const MdWs<T>& w, const uint8_t* s
     a.rtiles = (int)cdiv(a.R, kMdTile);
     a.ctiles = (int)cdiv(a.C, kMdTile);
     a.ksplit = w.ksplit;
-    const int smem = 2 * kMdTile * (M + 1) * (int)sizeof(T);
-    auto k = md_wgrad_kernel<T>;
-    if (int e = md_set_smem(k, smem)) return e;
-    prof_count(); k<<<dim3(a.rtiles * a.ctiles, a.ksplit), 256, smem, s>>>(g, a, w.partial);
-    RNNWF_CUDA(cudaGetLastError());
+    bool dmma_done = false;
+    if constexpr (std::is_same<T, double>::value) {
+        if (M % 2 == 0 && !getenv("RNNWF_WGRAD_FFMA")) {       // DMMA reduction (the reference's 2-D RNN computes in float64)
+            const int Rp = a.rtiles * kMdTile, Cp = a.ctiles * kMdTile;
+            const int64_t slots = ((int64_t)w.ksplit * w.Rp * w.Cp) / ((int64_t)Rp * Cp);
+            a.ksplit = wgdm::choose_ksplit(a.R, a.C, nblk, slots);
+            WgdmMdSrc src;
+            src.g = g; src.a = a; src.M = M; src.R = a.R; src.C = a.C; src.nblk = nblk;
+            auto k = wgdm::wgrad_kernel<WgdmMdSrc>;
+            if (int e = md_set_smem(k, (int)wgdm::kSmem)) return e;
+            const int ct = (int)cdiv(a.C, wgdm::kT);
+            prof_count(); k<<<dim3((int)cdiv(a.R, wgdm::kT) * ct, a.ksplit), wgdm::kThreads, wgdm::kSmem, s>>>(src, ct, a.ksplit, w.partial, Rp, Cp);
+            RNNWF_CUDA(cudaGetLastError());
+            dmma_done = true;
+        }
+    }
+    if (!dmma_done) {
+        const int smem = 2 * kMdTile * (M + 1) * (int)sizeof(T);
+        auto k = md_wgrad_kernel<T>;
+        if (int e = md_set_smem(k, smem)) return e;
+        prof_count(); k<<<dim3(a.rtiles * a.ctiles, a.ksplit), 256, smem, s>>>(g, a, w.partial);
+        RNNWF_CUDA(cudaGetLastError());
+    }
     prof_count(); md_wgrad_scatter_kernel<<<md_grid_for((int64_t)a.R * a.C), 256, 0, s>>>(g, w.partial, a.ksplit, a.rtiles * kMdTile,
                                                                                       a.ctiles * kMdTile, a.head, a.R, a.C, grad);
     RNNWF_CUDA(cudaGetLastError());
