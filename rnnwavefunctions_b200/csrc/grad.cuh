@@ -818,6 +818,7 @@ template <typename T> struct GradWs {
     unsigned char* img16;   // weight image of the tensor-core base pass (FP32 probability-head models it supports)
     float* gstore;          // backward factors [tile][site][layer]{[unit][M][4], [unit][M]} written by that pass for the tensor-core recurrence
     unsigned char* img16b;  // transposed-weight images of the tensor-core backward recurrence (gru_tc16b.cuh)
+    double* wb64;           // float64 one-layer stacks: operands of the DMMA base pass
     int ksplit, Rp, Cp;
 };
 
@@ -840,6 +841,9 @@ static GradWs<T> carve_grad(Ws& ws, const GruLayout& g, const GruLayoutT& gt, co
     w.partial = ws.take<double>((size_t)w.ksplit * w.Rp * w.Cp);
     w.img16 = nullptr;
     if (std::is_same<T, float>::value && !cplx && tc16p::supported(g)) w.img16 = ws.take<unsigned char>(tc16p::make_layout(g).img_bytes);
+    w.wb64 = nullptr;        // float64 one-layer stacks: B fragments + table of the DMMA base pass (gru_f64mma.cuh)
+    if (std::is_same<T, double>::value && !cplx && f64mma::supported(g))
+        w.wb64 = ws.take<double>(f64mma::make_layout(g).wb_doubles + f64mma::make_layout(g).tab_doubles);
     w.gstore = nullptr;
     w.img16b = nullptr;
     if (tc_bwd) {
@@ -999,6 +1003,14 @@ int gru_vmc_grad_t(const rnnwf_model& m, const void* params, const uint8_t* samp
             tc_bwd = b.tc != 0 && w.gstore != nullptr;
             e = tc16p::launch_eloc(g, b.M, tiles, (const float*)params, w.img16, w.f.sigT, w.f.hstore, w.f.la_sel, w.f.la_oth, w.f.la_self,
                                    w.f.lp_re, nullptr, w.f.counter, false, s, tc_bwd ? w.gstore : nullptr);
+            stashed = true;
+        }
+    }
+    if constexpr (std::is_same<T, double>::value) {
+        const char* env = getenv("RNNWF_CHAIN");
+        if (w.wb64 && !(env && strcmp(env, "ffma") == 0)) {      // float64 one-layer stacks: the DMMA base pass
+            e = f64mma::launch(g, b.M, rows_total, (const double*)params, w.wb64, w.wb64 + f64mma::make_layout(g).wb_doubles, w.f.sigT, w.f.hstore,
+                               w.f.la_sel, w.f.la_oth, w.f.lp_re, nullptr, w.f.counter, true, false, s);
             stashed = true;
         }
     }

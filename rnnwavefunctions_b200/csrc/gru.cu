@@ -502,18 +502,18 @@ int gru_tfim_eloc_t(const rnnwf_model& m, const void* params, const uint8_t* sam
         }
 #endif
     } else if (bx != 0.0) {   // reference skips the off-diagonal work when Bx == 0 (1DTFIM/TrainingRNN_1DTFIM.py:42)
-        if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
         const char* env = getenv("RNNWF_CHAIN");
         bool dmma_done = false;
         if constexpr (std::is_same<T, double>::value) {
-            if (wb64 && !(env && strcmp(env, "ffma") == 0)) {   // DMMA chain kernel; RNNWF_CHAIN=ffma keeps the thread-tile engine (A/B)
+            if (wb64 && !(env && strcmp(env, "ffma") == 0)) {   // DMMA base pass + chain kernel; RNNWF_CHAIN=ffma keeps the thread-tile engine (A/B)
                 if (int e = f64mma::launch(g, c.M, (int64_t)tiles * c.M, (const double*)params, wb64, wb64 + f64mma::make_layout(g).wb_doubles, w.sigT,
-                                           w.hstore, w.la_sel, w.la_oth, w.delta_re, w.counter, s))
+                                           w.hstore, w.la_sel, w.la_oth, w.lp_re, w.delta_re, w.counter, true, true, s))
                     return e;
                 dmma_done = true;
             }
         }
         if (!dmma_done) {
+            if (int e = launch_forward<T, true, false>(g, c, w, tiles, s)) return e;
             ChainPlan plan{g.N, g.N, 0, 0, tiles, nullptr, nullptr};
             if (int e = launch_chain<T, false>(g, c, plan, w, s)) return e;
         }

@@ -12,7 +12,8 @@
 // the three gate tiles r | u | ch over K = H in registers; the one-hot input part and the biases are table lookups that initialise the
 // accumulators; gates, new state and the restaging into the other hidden-state buffer happen in registers.  The two logits of the
 // Dense head ride in two spare columns of the last unit block's r tile (h_{n-1} Wd comes out of the GEMM of step n).
-// Same contract as gru_chain_kernel<double> (gru_kernels.cuh): restart states / per-site base terms in, delta[tile][slot][M] out.
+// Same contract as gru_chain_kernel<double> (gru_kernels.cuh): restart states / per-site base terms in, delta[tile][slot][M] out;
+// the BASE instantiation is the teacher-forced pass that produces them (contract of gru_forward_kernel<double, .., STASH>).
 // Included by gru.cu.
 #pragma once
 #include "gru_kernels.cuh"
@@ -38,7 +39,7 @@ inline Layout make_layout(const GruLayout& g) {
     t.head_block = t.blocks - 1;
     t.head_col = g.H - 8 * (t.blocks - 1);                        // first spare column of the last block (even)
     t.wb_doubles = (size_t)t.blocks * 3 * t.ksteps * 32;
-    t.tab_doubles = (size_t)8 * 8 * t.blocks;                     // [kind 0..6][unit]: r(s=0), r(s=1), u(0), u(1), cx(0), cx(1), ch-bias | bd[2] at the end
+    t.tab_doubles = (size_t)11 * 8 * t.blocks;                    // [kind][unit]: r(s=0), r(s=1), u(0), u(1), cx(0), cx(1), ch-bias | 7: bd[2] | 8..10: r, u, cx without input (site 0)
     return t;
 }
 
@@ -85,8 +86,10 @@ __global__ void pack_kernel(GruLayout g, Layout t, const double* __restrict__ fl
             else if (kind < 4) v = bg[H + j] + Kg[(kind - 2) * 2 * H + H + j];
             else if (kind < 6) v = bci[j] + Kci[(kind - 4) * H + j];
             else if (kind == 6) v = bch[j];
+            else v = 0.0;
         }
-        if (kind == 7 && j < 2) v = Wd[2 * H + j];                 // head bias
+        if (kind == 7) v = j < 2 ? Wd[2 * H + j] : 0.0;            // head bias
+        if (kind >= 8 && j < H) v = kind == 8 ? bg[j] : kind == 9 ? bg[H + j] : bci[j];   // zero input vector (site 0 of the base pass)
         tab[idx] = v;
     }
 }
@@ -99,8 +102,9 @@ struct Args {
     const double* wb;
     const double* tab;
     const uint8_t* sigT;
-    const double* hstore;
-    const double *la_sel, *la_oth;
+    double* hstore;               // FLIP: restart states (read); BASE: every site's state (written)
+    double *la_sel, *la_oth;      // FLIP: read at the flipped site and per site; BASE: written
+    double* lp;                   // BASE: sum_n la_sel
     double* delta;
     int* counter;
 };
@@ -109,6 +113,9 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// BASE: the teacher-forced pass over the unmodified configuration from the zero state (2DTFIM_1DRNN/RNNwavefunction.py:86-130):
+// stashes every site's state and per-site head terms (what the flip chains and the backward pass start from) and sums log P.
+template <bool BASE>
 __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constant__ Args a) {
     extern __shared__ __align__(16) unsigned char smem_f64[];
     __shared__ int s_work;
@@ -121,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
     const int qrow = lane >> 2, qcol = lane & 3;                              // fragment coordinates of this lane
     for (int i = tid; i < (int)t.tab_doubles; i += kThreads) tab[i] = a.tab[i];
     for (int i = tid; i < 2 * kRows * ldk; i += kThreads) hbuf[i] = 0.0;      // K padding columns stay zero
-    const int total = a.nslots * a.tiles64;
+    const int total = (BASE ? 1 : a.nslots) * a.tiles64;
     const bool head_warp = (2 * grp == t.head_block) || (2 * grp + 1 == t.head_block);
     const bool head_lane = head_warp && (2 * qcol == t.head_col);
 
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         __syncthreads();
         const int work = s_work;
         if (work >= total) break;
-        const int s = work / a.tiles64, tile = work % a.tiles64;              // slots in order of decreasing chain length
+        const int s = BASE ? -1 : work / a.tiles64, tile = work % a.tiles64;  // slots in order of decreasing chain length
         // this lane's four rows (one per m-tile): global row -> (old tile, row in tile) of the base pass' layout
         size_t rbase[4];       // index of (old tile, site 0, row): + n * Mold for site n
         size_t hbase[4];
@@ -147,16 +154,16 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             rbase[mt] = (size_t)otile[mt] * N * Mold + om[mt];
             hbase[mt] = 0;
         }
-        // restart state: h after site s of the base pass -> buffer 0
+        // restart state: h after site s of the base pass (BASE: the zero state) -> buffer 0
         for (int i = tid; i < kRows * H; i += kThreads) {
             const int row = i % kRows, j = i / kRows;
             int64_t R = (int64_t)tile * kRows + row;
             if (R >= a.rows_total) R = a.rows_total - 1;
             const size_t ot = (size_t)(R / Mold), m = (size_t)(R % Mold);
-            hbuf[row * ldk + j] = a.hstore[((ot * N + s) * H + j) * Mold + m];
+            hbuf[row * ldk + j] = BASE ? 0.0 : a.hstore[((ot * N + s) * H + j) * Mold + m];
         }
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        if (head_lane) {
+        if (!BASE && head_lane) {
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) acc[mt] = a.la_oth[rbase[mt] + (size_t)s * Mold] - a.la_sel[rbase[mt] + (size_t)s * Mold];
         }
@@ -165,14 +172,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         // steps n = s+1 .. N-1 compute h_n; step n == N only evaluates the head of site N-1
         for (int n = s + 1; n <= N; ++n) {
             // input spin of this step = spin of site n-1 of the connected configuration (flipped at s)
-            int sp[4];
+            int sp[4], kr[4], ku[4], kc[4];       // input spin (2: none, site 0 of the base pass) and the table rows of its constants
             double la_prev[4];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) {
-                int v = a.sigT[rbase[mt] + (size_t)(n - 1) * Mold];
-                if (n - 1 == s) v = 1 - v;
+                int v = n > 0 ? a.sigT[rbase[mt] + (size_t)(n - 1) * Mold] : 2;
+                if (!BASE && n - 1 == s) v = 1 - v;
                 sp[mt] = v;
-                la_prev[mt] = (head_lane && n - 1 > s) ? a.la_sel[rbase[mt] + (size_t)(n - 1) * Mold] : 0.0;
+                kr[mt] = v < 2 ? v : 8; ku[mt] = v < 2 ? 2 + v : 9; kc[mt] = v < 2 ? 4 + v : 10;
+                la_prev[mt] = (!BASE && head_lane && n - 1 > s) ? a.la_sel[rbase[mt] + (size_t)(n - 1) * Mold] : 0.0;
             }
             const double* hc = hbuf + (size_t)cur * kRows * ldk;
             double* hn = hbuf + (size_t)(cur ^ 1) * kRows * ldk;
@@ -188,8 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
                 for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
-                        cr[mt][e] = tab[(0 + sp[mt]) * U + j0 + e];
-                        cu[mt][e] = tab[(2 + sp[mt]) * U + j0 + e];
+                        cr[mt][e] = tab[kr[mt] * U + j0 + e];
+                        cu[mt][e] = tab[ku[mt] * U + j0 + e];
                         cq[mt][e] = tab[6 * U + j0 + e];
                     }
                 }
@@ -217,9 +225,17 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
                 if (b == t.head_block && head_lane && n - 1 > s) {
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt) {
-                        const double z0 = cr[mt][0] - tab[(0 + sp[mt]) * U + j0] + tab[7 * U], z1 = cr[mt][1] - tab[(0 + sp[mt]) * U + j0 + 1] + tab[7 * U + 1];
+                        const double z0 = cr[mt][0] - tab[kr[mt] * U + j0] + tab[7 * U], z1 = cr[mt][1] - tab[kr[mt] * U + j0 + 1] + tab[7 * U + 1];
                         const double ls = sp[mt] ? log_softmax2(z1, z0) : log_softmax2(z0, z1);
-                        acc[mt] += ls - la_prev[mt];
+                        if (BASE) {
+                            if (live[mt]) {
+                                a.la_sel[rbase[mt] + (size_t)(n - 1) * Mold] = ls;
+                                a.la_oth[rbase[mt] + (size_t)(n - 1) * Mold] = sp[mt] ? log_softmax2(z0, z1) : log_softmax2(z1, z0);
+                            }
+                            acc[mt] += ls;
+                        } else {
+                            acc[mt] += ls - la_prev[mt];
+                        }
                     }
                 }
                 if (last) continue;
@@ -234,10 +250,15 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
                         for (int e = 0; e < 2; ++e) {
                             const double r = sigmoid_(cr[mt][e]);
                             const double u = sigmoid_(cu[mt][e]);
-                            const double c = tanh_(fma(r, cq[mt][e], tab[(4 + sp[mt]) * U + j0 + e]));
+                            const double c = tanh_(fma(r, cq[mt][e], tab[kc[mt] * U + j0 + e]));
                             out[e] = fma(u, hv[e] - c, c);
                         }
                         *reinterpret_cast<double2*>(hn + (size_t)row * ldk + j0) = make_double2(out[0], out[1]);
+                        if (BASE && live[mt]) {
+                            double* hs = a.hstore + (((size_t)otile[mt] * N + n) * H + j0) * Mold + om[mt];
+                            hs[0] = out[0];
+                            hs[Mold] = out[1];
+                        }
                     }
                 }
             }
@@ -247,34 +268,55 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         if (head_lane) {
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
-                if (live[mt]) a.delta[((size_t)otile[mt] * a.nslots + s) * Mold + om[mt]] = acc[mt];
+                if (live[mt]) {
+                    if (BASE) a.lp[(size_t)otile[mt] * Mold + om[mt]] = acc[mt];
+                    else a.delta[((size_t)otile[mt] * a.nslots + s) * Mold + om[mt]] = acc[mt];
+                }
         }
         (void)hbase;
     }
 }
 
-static int launch(const GruLayout& g, int Mold, int64_t rows_total, const double* params, double* wb, double* tab, const uint8_t* sigT,
-                  const double* hstore, const double* la_sel, const double* la_oth, double* delta, int* counter, cudaStream_t s) {
+static Args make_args(const GruLayout& g, int Mold, int64_t rows_total, double* wb, double* tab, const uint8_t* sigT, double* hstore,
+                      double* la_sel, double* la_oth, double* lp, double* delta, int* counter) {
     Args a;
     memset(&a, 0, sizeof(a));
     a.g = g; a.t = make_layout(g); a.Mold = Mold; a.rows_total = rows_total;
     a.tiles64 = (int)cdiv(rows_total, kRows);
     a.nslots = g.N;
-    a.wb = wb; a.tab = tab; a.sigT = sigT; a.hstore = hstore; a.la_sel = la_sel; a.la_oth = la_oth; a.delta = delta; a.counter = counter;
+    a.wb = wb; a.tab = tab; a.sigT = sigT; a.hstore = hstore; a.la_sel = la_sel; a.la_oth = la_oth; a.lp = lp; a.delta = delta; a.counter = counter;
+    return a;
+}
+
+// teacher-forced base pass with stash (rows in the [tile][site][..][Mold] layout of the thread-tile engine) and, with `flips`, the
+// single-flip chains from it
+static int launch(const GruLayout& g, int Mold, int64_t rows_total, const double* params, double* wb, double* tab, const uint8_t* sigT,
+                  double* hstore, double* la_sel, double* la_oth, double* lp, double* delta, int* counter, bool base, bool flips,
+                  cudaStream_t s) {
+    Args a = make_args(g, Mold, rows_total, wb, tab, sigT, hstore, la_sel, la_oth, lp, delta, counter);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int smem = (int)smem_bytes(a.t);
     RNNWF_CHECK(smem <= kSmemLimit, -3, "float64 DMMA chain kernel needs %d bytes of shared memory", smem);
     prof_count(); pack_kernel<<<148, 256, 0, s>>>(g, a.t, params, wb, tab);
-    RNNWF_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
-    RNNWF_CUDA(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = (int)std::min<int64_t>((int64_t)a.nslots * a.tiles64, sms);
-    prof_count();
-    prof_mark(0, s);
-    chain_kernel<<<grid, kThreads, smem, s>>>(a);
-    prof_mark(1, s);
-    RNNWF_CUDA(cudaGetLastError());
+    if (base) {
+        RNNWF_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
+        RNNWF_CUDA(cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        prof_count();
+        chain_kernel<true><<<std::min(a.tiles64, sms), kThreads, smem, s>>>(a);
+        RNNWF_CUDA(cudaGetLastError());
+    }
+    if (flips) {
+        RNNWF_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), s));
+        RNNWF_CUDA(cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid = (int)std::min<int64_t>((int64_t)a.nslots * a.tiles64, sms);
+        prof_count();
+        prof_mark(0, s);
+        chain_kernel<false><<<grid, kThreads, smem, s>>>(a);
+        prof_mark(1, s);
+        RNNWF_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 
