@@ -706,8 +706,10 @@ struct WgdmGruSrc {
     WgradArgs<double> a;
     int M, R, C;
     int64_t nblk;
-    __device__ __forceinline__ const double* a_src(int64_t blk, int r, int k, bool& special, double& v0, double& v1) const {
-        const int n = (int)(blk % a.N);
+    struct Ctx { int n; };
+    __device__ __forceinline__ Ctx begin(int64_t blk) const { return Ctx{(int)(blk % a.N)}; }
+    __device__ __forceinline__ const double* a_src(const Ctx& cx, int64_t blk, int r, int k, bool& special, double& v0, double& v1) const {
+        const int n = cx.n;
         if (r < a.rows0) {
             if (a.xmode == 1) return a.hstore + ((blk * a.L + a.lx) * a.H + r) * M + k;
             special = true;                                                // one-hot input row: sigma of the site before
@@ -725,7 +727,7 @@ struct WgdmGruSrc {
         v0 = v1 = 1.0;
         return nullptr;
     }
-    __device__ __forceinline__ const double* b_src(int64_t blk, int c, int k) const { return a.B + (blk * a.cols + c) * M + k; }
+    __device__ __forceinline__ const double* b_src(const Ctx&, int64_t blk, int c, int k) const { return a.B + (blk * a.cols + c) * M + k; }
 };
 
 // sum the split-K partials (fixed order) and scatter into the flat gradient.

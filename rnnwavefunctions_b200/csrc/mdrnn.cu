@@ -537,7 +537,15 @@ struct WgdmMdSrc {
     MdWgArgs<double> a;
     int M, R, C;
     int64_t nblk;
-    __device__ __forceinline__ const double* a_src(int64_t blk, int r, int k, bool& special, double& v0, double& v1) const {
+    struct Ctx { int64_t st; int pl, pu; };
+    __device__ __forceinline__ Ctx begin(int64_t blk) const {          // neighbours of the position of block blk on the zig-zag path
+        Ctx c;
+        c.st = blk / g.N;
+        int x, y, pd;
+        md_decode(g, (int)(blk % g.N), x, y, c.pl, c.pu, pd);
+        return c;
+    }
+    __device__ __forceinline__ const double* a_src(const Ctx& cx, int64_t blk, int r, int k, bool& special, double& v0, double& v1) const {
         const int H = g.H, N = g.N;
         if (a.head) {
             if (r < H) return a.hgrid + ((size_t)blk * H + r) * M + k;
@@ -545,10 +553,8 @@ struct WgdmMdSrc {
             v0 = v1 = 1.0;
             return nullptr;
         }
-        const int p = (int)(blk % N);
-        const int64_t st = blk / N;
-        int x, y, pl, pu, pd;
-        md_decode(g, p, x, y, pl, pu, pd);
+        const int64_t st = cx.st;
+        const int pl = cx.pl, pu = cx.pu;
         if (r < H) return pl >= 0 ? a.hgrid + (((size_t)st * N + pl) * H + r) * M + k : nullptr;
         if (r < 2 * H) return pu >= 0 ? a.hgrid + (((size_t)st * N + pu) * H + (r - H)) * M + k : nullptr;
         special = true;
@@ -565,7 +571,7 @@ struct WgdmMdSrc {
         }
         return nullptr;
     }
-    __device__ __forceinline__ const double* b_src(int64_t blk, int c, int k) const { return a.B + ((size_t)blk * a.C + c) * M + k; }
+    __device__ __forceinline__ const double* b_src(const Ctx&, int64_t blk, int c, int k) const { return a.B + ((size_t)blk * a.C + c) * M + k; }
 };
 
 __global__ void md_wgrad_scatter_kernel(MdLayout g, const double* __restrict__ partial, int ksplit, int Rp, int Cp, int head, int R,

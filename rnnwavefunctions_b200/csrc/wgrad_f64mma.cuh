@@ -13,10 +13,11 @@
 //
 // Src describes the operands of one model family:
 //   int M, R, C; int64_t nblk;
-//   const double* a_src(int64_t blk, int r, int k, bool& special, double& v0, double& v1) const
+//   Ctx begin(int64_t blk) const      what is common to every element of block blk (site index, neighbour positions, ...)
+//   const double* a_src(const Ctx&, int64_t blk, int r, int k, bool& special, double& v0, double& v1) const
 //        address of A[r][k], A[r][k + 1] of block blk (nullptr: zeros), or special = true with the two values computed (one-hot rows,
 //        the constant-1 row);  k is even and k < M
-//   const double* b_src(int64_t blk, int c, int k) const
+//   const double* b_src(const Ctx&, int64_t blk, int c, int k) const
 #pragma once
 #include "gru_engine.cuh"
 
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(Src src, int ct, int
     auto issue = [&](int64_t t) {      // K slice t of this CTA -> stage t % kStages
         const int64_t blk = b0 + t / nsl;
         const int k0 = (int)(t % nsl) * kKS;
+        const auto ctx = src.begin(blk);
         double* A = buf + (size_t)(t % kStages) * kStageDoubles;
         double* B = A + kT * kMS;
         for (int i = tid; i < 2 * kT * (kKS / 2); i += kThreads) {
@@ -64,13 +66,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(Src src, int ct, int
                 if (row < kT) {
                     bool special = false;
                     double v0 = 0.0, v1 = 0.0;
-                    if (r0 + row < src.R) p = src.a_src(blk, r0 + row, k, special, v0, v1);
+                    if (r0 + row < src.R) p = src.a_src(ctx, blk, r0 + row, k, special, v0, v1);
                     if (special) {
                         *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
                         continue;
                     }
                 } else if (c0 + row - kT < src.C) {
-                    p = src.b_src(blk, c0 + row - kT, k);
+                    p = src.b_src(ctx, blk, c0 + row - kT, k);
                 }
             }
             if (p != nullptr) cp_async16(dst, p);
