@@ -100,3 +100,20 @@ def test_lr_schedules_match_the_reference_formulas():
     assert inspect.signature(TR.run_2DTFIM_1DRNN).parameters["lr_schedule"].default == "inverse"
     assert inspect.signature(TR.run_2DTFIM_2DRNN).parameters["lr_schedule"].default == "inverse5000"
     assert inspect.signature(TR.run_J1J2).parameters["lr_schedule"].default is None
+
+
+def test_sample_slices_fit_the_workspace_budget(lib, monkeypatch):
+    """Host logic of ops.sample_chunk (no GPU needed: rnnwf_workspace_bytes is host arithmetic): the slice is the largest multiple of
+    256 samples whose workspace fits RNNWF_WS_BUDGET_GB; batches that fit are not sliced."""
+    from rnnwavefunctions_b200 import ops
+    m = ops.make_model(num_layers=3, units=50, n_sites=1000)
+    ns = 100_000
+    need = ops.workspace_bytes(m, ops.OP_VMC_GRAD, ns)
+    assert need > 400e9                                   # ~47 GB per 10^4 samples at cfg2: does not fit one B200
+    monkeypatch.setenv("RNNWF_WS_BUDGET_GB", "100")
+    step = ops.sample_chunk(m, ops.OP_VMC_GRAD, ns, 0, "cuda:0")
+    assert 0 < step < ns and step % 256 == 0
+    assert ops.workspace_bytes(m, ops.OP_VMC_GRAD, step) <= 100 * 2 ** 30 < ops.workspace_bytes(m, ops.OP_VMC_GRAD, step + 256)
+    assert ops.sample_chunk(m, ops.OP_TFIM_ELOC, 10_000, 0, "cuda:0") == 10_000      # 6.3 GB: fits
+    par = ops.sample_chunk(m, ops.OP_TFIM_ELOC, ns, ops.PARITY_SYM, "cuda:0")
+    assert par < ops.sample_chunk(m, ops.OP_TFIM_ELOC, ns, 0, "cuda:0")             # both directions of every chain
