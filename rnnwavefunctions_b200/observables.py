@@ -57,7 +57,7 @@ def sigma_x(wf, samples, return_error=False):
     su8 = _u8(wf, samples)
     N = wf.model.n_sites
     jz = torch.zeros(N, dtype=torch.float64, device=wf.device)
-    _, _, ratios = ops.tfim_flip_ratios(wf.model, wf.params, su8, jz, 1.0, wf._flags)
+    _, _, ratios = ops.tfim_flip_ratios(wf.model, wf.kernel_params, su8, jz, 1.0, wf._flags)
     mean = ratios.mean(0)
     if return_error:
         return mean, ratios.std(0, unbiased=True) / np.sqrt(ratios.shape[0])
@@ -66,7 +66,7 @@ def sigma_x(wf, samples, return_error=False):
 
 def _log_psi(wf, su8):
     """log psi as a complex tensor [ns]: 0.5 log P for the positive models, log amplitude + i phase for the cRNN."""
-    out = ops.logpsi(wf.model, wf.params, su8, wf._flags)
+    out = ops.logpsi(wf.model, wf.kernel_params, su8, wf._flags)
     if wf.model.head == HEAD_COMPLEX:
         return out                                   # complex128: log amplitude + i phase
     return torch.complex(0.5 * out, torch.zeros_like(out))

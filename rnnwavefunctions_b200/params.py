@@ -35,6 +35,51 @@ def gru_shapes(units, inputdim=2, heads=("wf_dense",), scope=SCOPE):
     return shapes
 
 
+def gru_pad_index(units, inputdim=2, heads=("wf_dense",), scope=SCOPE):
+    """Unequal layer widths (`MultiRNNCell([cell(units[n]) for n ...])`, 1DTFIM/RNNwavefunction.py:32, accepts any list) run on the
+    equal-width kernels zero-padded to the widest layer: a padded unit has zero weights and biases in and out, so its gates are
+    exactly 1/2, its candidate exactly 0 and its state stays exactly 0; nothing of it reaches a real unit.
+    -> (index, padded_count): index[i] = position of element i of the real flat vector (TF order) in the padded flat vector."""
+    units = [int(u) for u in units]
+    H = max(units)
+    real, padded = gru_shapes(units, inputdim, heads, scope), gru_shapes([H] * len(units), inputdim, heads, scope)
+    base, o = {}, 0
+    for name, shape in padded.items():
+        base[name] = o
+        o += int(np.prod(shape))
+    padded_count = o
+
+    def pos(segments):          # [(real length, offset in the padded axis), ...] -> padded positions of the real entries
+        return np.concatenate([off + np.arange(n) for n, off in segments]).astype(np.int64)
+
+    idx = []
+    d = inputdim
+    for l, h in enumerate(units):
+        D = inputdim if l == 0 else H
+        pre = f"{scope}/multi_rnn_cell/cell_{l}/cudnn_compatible_gru_cell/"
+        axes = {
+            pre + "gates/kernel": ([(d, 0), (h, D)], [(h, 0), (h, H)]),
+            pre + "gates/bias": (None, [(h, 0), (h, H)]),
+            pre + "candidate/input_projection/kernel": ([(d, 0)], [(h, 0)]),
+            pre + "candidate/hidden_projection/kernel": ([(h, 0)], [(h, 0)]),
+            pre + "candidate/input_projection/bias": (None, [(h, 0)]),
+            pre + "candidate/hidden_projection/bias": (None, [(h, 0)]),
+        }
+        for name, (rows, cols) in axes.items():
+            c = pos(cols)
+            if rows is None:
+                idx.append(base[name] + c)
+            else:
+                idx.append((base[name] + pos(rows)[:, None] * padded[name][1] + c[None, :]).reshape(-1))
+        d = h
+    for head in heads:
+        idx.append((base[f"{scope}/{head}/kernel"] + np.arange(units[-1])[:, None] * 2 + np.arange(2)[None, :]).reshape(-1))
+        idx.append(base[f"{scope}/{head}/bias"] + np.arange(2))
+    index = np.concatenate(idx)
+    assert index.size == count(real) and len(np.unique(index)) == index.size and index.max() < padded_count
+    return index, padded_count
+
+
 def mdrnn_shapes(h, inputdim=2, scope=SCOPE):
     """MDRNNcell variables (2DTFIM_2DRNN/MDRNNcell.py:21-35, name 'rnn_0' from RNNwavefunction.py:32) + Dense."""
     shapes = OrderedDict()

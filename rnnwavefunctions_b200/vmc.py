@@ -42,7 +42,7 @@ class TFIM:
         return t
 
     def local_energies(self, wf, samples_u8, want_logp=False):
-        e, lp = ops.tfim_eloc(wf.model, wf.params, samples_u8, self._jz(wf.params.device), self.Bx, wf._flags, want_logp=want_logp)
+        e, lp = ops.tfim_eloc(wf.model, wf.kernel_params, samples_u8, self._jz(wf.params.device), self.Bx, wf._flags, want_logp=want_logp)
         return (e, lp) if want_logp else e
 
 
@@ -64,7 +64,7 @@ class J1J2:
 
     def local_energies(self, wf, samples_u8, want_logp=False):
         j1, j2, bz = self._arrs(wf.params.device)
-        e, la = ops.j1j2_eloc(wf.model, wf.params, samples_u8, j1, j2, bz, self.marshall_sign, want_logpsi=want_logp)
+        e, la = ops.j1j2_eloc(wf.model, wf.kernel_params, samples_u8, j1, j2, bz, self.marshall_sign, want_logpsi=want_logp)
         return (e, la) if want_logp else e
 
 
@@ -92,7 +92,7 @@ class VMC:
 
     # -- stages (each one is a C-ABI call; bench.py times them separately) -----------------------
     def draw(self):
-        return ops.sample(self.wf.model, self.wf.params, self.ns, self.wf._next_seed(), self.wf.sample_offset)
+        return ops.sample(self.wf.model, self.wf.kernel_params, self.ns, self.wf._next_seed(), self.wf.sample_offset)
 
     def local_energies(self, samples_u8):
         return self.H.local_energies(self.wf, samples_u8)
@@ -116,7 +116,7 @@ class VMC:
     def gradient(self, samples_u8, eloc, mean, n):
         scale = 2.0 if self.complex else 1.0       # complex cost carries the factor 2 (J1J2/TrainingRNN_J1J2.py:197)
         w = (eloc - mean) * (scale / n)
-        g = ops.vmc_grad(self.wf.model, self.wf.params, samples_u8, w, self.wf._flags)
+        g = self.wf.unpad_gradient(ops.vmc_grad(self.wf.model, self.wf.kernel_params, samples_u8, w, self.wf._flags))
         if self.world > 1:
             self.dist.all_reduce(g, op=self.dist.ReduceOp.SUM, group=self.group)
         return g

@@ -70,7 +70,7 @@ class _WavefunctionBase:
 
     _flags = 0
 
-    def _setup(self, model, shapes, seed, device, mdrnn=False):
+    def _setup(self, model, shapes, seed, device, mdrnn=False, pad=None):
         self.model = model
         self.shapes = shapes
         self.device = _device(device)
@@ -78,7 +78,16 @@ class _WavefunctionBase:
         self.dtype = torch.float32 if model.dtype == F32 else torch.float64
         npdtype = np.float32 if model.dtype == F32 else np.float64
         self.params = torch.tensor(P.init_flat(shapes, seed, npdtype, mdrnn=mdrnn), device=self.device)
-        assert self.params.numel() == ops.param_count(model), (self.params.numel(), ops.param_count(model))
+        # unequal layer widths: the kernels see the stack zero-padded to its widest layer (params.gru_pad_index); `params` stays the
+        # real TF-order vector (what the optimiser updates and what .npz files hold)
+        self._pad_index, self._kbuf = None, None
+        if pad is not None:
+            index, padded_count = pad
+            assert padded_count == ops.param_count(model), (padded_count, ops.param_count(model))
+            self._pad_index = torch.as_tensor(index, device=self.device)
+            self._kbuf = torch.zeros(padded_count, dtype=self.dtype, device=self.device)
+        else:
+            assert self.params.numel() == ops.param_count(model), (self.params.numel(), ops.param_count(model))
         if model.cell == CELL_GRU and model.dtype == F32 and model.units > 50 and ops.tfim_chain_mode(model) == 0:
             import warnings
             warnings.warn(f"float32 GRU stacks wider than 50 units (here {model.units}) evaluate local energies on the CUDA-core FFMA engine, "
@@ -94,6 +103,18 @@ class _WavefunctionBase:
     @property
     def num_params(self):
         return self.params.numel()
+
+    @property
+    def kernel_params(self):
+        """The flat parameter vector the CUDA kernels consume: `params` itself, or its zero-padded image (unequal layer widths)."""
+        if self._pad_index is None:
+            return self.params
+        self._kbuf.index_copy_(0, self._pad_index, self.params)      # padding entries are never written: they stay zero
+        return self._kbuf
+
+    def unpad_gradient(self, grad):
+        """Gradient with respect to `params` from the kernels' gradient with respect to `kernel_params`."""
+        return grad if self._pad_index is None else grad.index_select(0, self._pad_index)
 
     def named_parameters(self):
         return P.split_flat(self.params.detach().cpu().numpy(), self.shapes)
@@ -125,18 +146,17 @@ class RNNwavefunction1D(_WavefunctionBase):
     """1-D positive RNN wave function: stacked GRU + Dense(2)+softmax (1DTFIM/RNNwavefunction.py:8-33)."""
 
     def __init__(self, systemsize, cell=None, units=[10], scope="RNNwavefunction", seed=111, device=None):
-        if len(set(units)) != 1:
-            raise NotImplementedError("the CUDA kernels need equal layer widths (as every run_* driver of the reference uses)")
         self.N = systemsize
         self.scope = scope
-        model = ops.make_model(CELL_GRU, HEAD_PROB, F32, len(units), units[0], systemsize)
-        self._setup(model, P.gru_shapes(list(units), scope=scope), seed, device)
+        model = ops.make_model(CELL_GRU, HEAD_PROB, F32, len(units), max(units), systemsize)
+        pad = P.gru_pad_index(units, scope=scope) if len(set(units)) != 1 else None
+        self._setup(model, P.gru_shapes(list(units), scope=scope), seed, device, pad=pad)
 
     def sample(self, numsamples, inputdim=2):
         """-> int64 CUDA tensor [numsamples, N] of 0/1 (1DTFIM/RNNwavefunction.py:35-74)."""
         assert inputdim == 2
         self.numsamples, self.inputdim, self.outputdim = numsamples, inputdim, inputdim
-        self._last_u8 = ops.sample(self.model, self.params, numsamples, self._next_seed(), self.sample_offset)
+        self._last_u8 = ops.sample(self.model, self.kernel_params, numsamples, self._next_seed(), self.sample_offset)
         self.samples = self._last_u8.to(torch.int64)
         self.samples._rnnwf_u8 = self._last_u8
         return self.samples
@@ -144,7 +164,7 @@ class RNNwavefunction1D(_WavefunctionBase):
     def log_probability(self, samples, inputdim=2):
         """-> float64 CUDA tensor [numsamples] (1DTFIM/RNNwavefunction.py:76-118)."""
         assert inputdim == 2
-        self.log_probs = ops.logpsi(self.model, self.params, self._u8(samples), self._flags)
+        self.log_probs = ops.logpsi(self.model, self.kernel_params, self._u8(samples), self._flags)
         return self.log_probs
 
 
@@ -160,13 +180,12 @@ class RNNwavefunction2DFlat(RNNwavefunction1D):
 
     def __init__(self, systemsize_x, systemsize_y, cell=None, activation=None, units=[10], scope="RNNwavefunction", seed=111,
                  device=None):
-        if len(set(units)) != 1:
-            raise NotImplementedError("the CUDA kernels need equal layer widths")
         self.Nx, self.Ny = systemsize_x, systemsize_y
         self.N = systemsize_x * systemsize_y
         self.scope = scope
-        model = ops.make_model(CELL_GRU, HEAD_PROB, F64, len(units), units[0], self.N, systemsize_x, systemsize_y)
-        self._setup(model, P.gru_shapes(list(units), scope=scope), seed, device)
+        model = ops.make_model(CELL_GRU, HEAD_PROB, F64, len(units), max(units), self.N, systemsize_x, systemsize_y)
+        pad = P.gru_pad_index(units, scope=scope) if len(set(units)) != 1 else None
+        self._setup(model, P.gru_shapes(list(units), scope=scope), seed, device, pad=pad)
 
 
 class MDRNNcell:
@@ -219,14 +238,14 @@ class RNNwavefunction2D(_WavefunctionBase):
     def sample(self, numsamples, inputdim=2):
         assert inputdim == 2
         self.numsamples, self.inputdim, self.outputdim = numsamples, inputdim, inputdim
-        self._last_u8 = ops.sample(self.model, self.params, numsamples, self._next_seed(), self.sample_offset)
+        self._last_u8 = ops.sample(self.model, self.kernel_params, numsamples, self._next_seed(), self.sample_offset)
         self.samples = self._last_u8.to(torch.int64).reshape(numsamples, self.Nx, self.Ny)
         self.samples._rnnwf_u8 = self._last_u8
         return self.samples
 
     def log_probability(self, samples, inputdim=2):
         assert inputdim == 2
-        self.log_probs = ops.logpsi(self.model, self.params, self._u8(samples), 0)
+        self.log_probs = ops.logpsi(self.model, self.kernel_params, self._u8(samples), 0)
         return self.log_probs
 
 
@@ -234,20 +253,20 @@ class ComplexRNNwavefunction(_WavefunctionBase):
     """Complex RNN wave function with U(1) zero-magnetisation masking (J1J2/ComplexRNNwavefunction.py:16-43)."""
 
     def __init__(self, systemsize, cell=None, units=[10, 10], scope="RNNwavefunction", seed=111, device=None):
-        if len(set(units)) != 1:
-            raise NotImplementedError("the CUDA kernels need equal layer widths")
         if systemsize % 2:
             raise ValueError("zero magnetisation needs an even number of sites (SURVEY.md B10)")
         self.N = systemsize
         self.scope = scope
-        model = ops.make_model(CELL_GRU, HEAD_COMPLEX, F32, len(units), units[0], systemsize)
-        self._setup(model, P.gru_shapes(list(units), heads=("wf_dense_ampl", "wf_dense_phase"), scope=scope), seed, device)
+        model = ops.make_model(CELL_GRU, HEAD_COMPLEX, F32, len(units), max(units), systemsize)
+        heads = ("wf_dense_ampl", "wf_dense_phase")
+        pad = P.gru_pad_index(units, heads=heads, scope=scope) if len(set(units)) != 1 else None
+        self._setup(model, P.gru_shapes(list(units), heads=heads, scope=scope), seed, device, pad=pad)
 
     def sample(self, numsamples, inputdim=2):
         """-> int64 [numsamples, N], every row has N/2 up spins (ComplexRNNwavefunction.py:45-103)."""
         assert inputdim == 2
         self.numsamples, self.inputdim, self.outputdim = numsamples, inputdim, inputdim
-        self._last_u8 = ops.sample(self.model, self.params, numsamples, self._next_seed(), self.sample_offset)
+        self._last_u8 = ops.sample(self.model, self.kernel_params, numsamples, self._next_seed(), self.sample_offset)
         self.samples = self._last_u8.to(torch.int64)
         self.samples._rnnwf_u8 = self._last_u8
         return self.samples
@@ -255,7 +274,7 @@ class ComplexRNNwavefunction(_WavefunctionBase):
     def log_amplitude(self, samples, inputdim=2):
         """-> complex128 CUDA tensor [numsamples] (reference: complex64, ComplexRNNwavefunction.py:105-169)."""
         assert inputdim == 2
-        self.log_amplitudes = ops.logpsi(self.model, self.params, self._u8(samples), 0)
+        self.log_amplitudes = ops.logpsi(self.model, self.kernel_params, self._u8(samples), 0)
         return self.log_amplitudes
 
 

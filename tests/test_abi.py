@@ -117,3 +117,41 @@ def test_sample_slices_fit_the_workspace_budget(lib, monkeypatch):
     assert ops.sample_chunk(m, ops.OP_TFIM_ELOC, 10_000, 0, "cuda:0") == 10_000      # 6.3 GB: fits
     par = ops.sample_chunk(m, ops.OP_TFIM_ELOC, ns, ops.PARITY_SYM, "cuda:0")
     assert par < ops.sample_chunk(m, ops.OP_TFIM_ELOC, ns, 0, "cuda:0")             # both directions of every chain
+
+
+def test_unequal_layer_widths_embed_into_the_padded_layout():
+    """params.gru_pad_index: the real TF-order vector of a stack with unequal widths lands in the top-left blocks of the equal-width
+    layout of its widest layer; everything else stays zero (host logic of the zero-padding path, 1DTFIM/RNNwavefunction.py:32)."""
+    import numpy as np
+
+    from rnnwavefunctions_b200 import params as P
+    for units, heads in (([5, 3, 4], ("wf_dense",)), ([3, 6], ("wf_dense_ampl", "wf_dense_phase")), ([7, 2], ("wf_dense",))):
+        H = max(units)
+        real_shapes, pad_shapes = P.gru_shapes(units, heads=heads), P.gru_shapes([H] * len(units), heads=heads)
+        index, padded_count = P.gru_pad_index(units, heads=heads)
+        assert padded_count == P.count(pad_shapes)
+        flat = np.arange(1, P.count(real_shapes) + 1, dtype=np.float64)
+        padded = np.zeros(padded_count)
+        padded[index] = flat
+        real, pad = P.split_flat(flat, real_shapes), P.split_flat(padded, pad_shapes)
+        d = 2
+        for l, h in enumerate(units):
+            D = 2 if l == 0 else H
+            pre = f"RNNwavefunction/multi_rnn_cell/cell_{l}/cudnn_compatible_gru_cell/"
+            Kg, Kp = real[pre + "gates/kernel"], pad[pre + "gates/kernel"]
+            assert np.array_equal(Kp[:d, :h], Kg[:d, :h]) and np.array_equal(Kp[:d, H:H + h], Kg[:d, h:])         # input rows: r | u
+            assert np.array_equal(Kp[D:D + h, :h], Kg[d:, :h]) and np.array_equal(Kp[D:D + h, H:H + h], Kg[d:, h:])   # hidden rows
+            assert np.count_nonzero(Kp) == Kg.size
+            bg, bp = real[pre + "gates/bias"], pad[pre + "gates/bias"]
+            assert np.array_equal(bp[:h], bg[:h]) and np.array_equal(bp[H:H + h], bg[h:]) and np.count_nonzero(bp) == bg.size
+            for name in ("candidate/input_projection/kernel", "candidate/hidden_projection/kernel"):
+                a, b = real[pre + name], pad[pre + name]
+                assert np.array_equal(b[:a.shape[0], :a.shape[1]], a) and np.count_nonzero(b) == a.size
+            for name in ("candidate/input_projection/bias", "candidate/hidden_projection/bias"):
+                a, b = real[pre + name], pad[pre + name]
+                assert np.array_equal(b[:h], a) and np.count_nonzero(b) == a.size
+            d = h
+        for head in heads:
+            a, b = real[f"RNNwavefunction/{head}/kernel"], pad[f"RNNwavefunction/{head}/kernel"]
+            assert np.array_equal(b[:units[-1]], a) and np.count_nonzero(b) == a.size
+            assert np.array_equal(pad[f"RNNwavefunction/{head}/bias"], real[f"RNNwavefunction/{head}/bias"])

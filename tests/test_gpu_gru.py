@@ -241,3 +241,45 @@ def test_f64_one_layer_eloc_dmma_and_thread_tile_kernels_agree_with_oracle(H, nx
     refp = O.ising2d_local_energies(Jz, 1.7, nx, ny, s, lambda c: O.log_probability_parity(p, c), flat=True)
     ep, _ = ops.tfim_eloc(model, flat, u8(s), Jz, 1.7, flags=ops.PARITY_SYM)
     np.testing.assert_allclose(ep.cpu().numpy(), refp, rtol=1e-10)
+
+
+@pytest.mark.parametrize("units,dtype", [([50, 30, 40], "f32"), ([6, 9], "f32"), ([12, 7], "f64")])
+def test_unequal_layer_widths_run_zero_padded(units, dtype):
+    """`units` may be any list (MultiRNNCell([cell(units[n]) ...]), 1DTFIM/RNNwavefunction.py:32): the kernels see the stack zero-padded to
+    its widest layer; log-probability, sampler, local energies, gradient and one optimiser step against the oracle at the real widths."""
+    from oracle import torch_grad as TG
+    from rnnwavefunctions_b200.vmc import TFIM, VMC
+    from rnnwavefunctions_b200.wavefunction import RNNwavefunction1D, RNNwavefunction2DFlat
+    N, ns = 12, 200
+    if dtype == "f32":
+        wf, npd, tol = RNNwavefunction1D(N, units=units, seed=5), np.float32, 1e-5
+        H = TFIM(np.ones(N), 1.0)
+    else:
+        wf, npd, tol = RNNwavefunction2DFlat(3, 4, units=units, seed=5), np.float64, 1e-10
+        H = TFIM(np.ones((3, 4)), 1.0)
+    assert wf.num_params == sum(int(np.prod(s)) for s in O.gru_param_shapes(units).values())
+    rng = np.random.default_rng(1)
+    wf.params.copy_(torch.tensor(wf.params.cpu().numpy() + rng.uniform(-0.3, 0.3, wf.num_params).astype(npd), device=wf.device))
+    p = O.unflatten(wf.params.cpu().numpy(), O.gru_param_shapes(units), npd)
+    opt = VMC(wf, H, ns)
+    s = opt.draw()
+    s_h = s.cpu().numpy().astype(np.int64)
+    lp = wf.log_probability(s_h).cpu().numpy()
+    np.testing.assert_allclose(lp, O.log_probability(p, s_h), rtol=tol)
+    probs = O.gru_conditionals(p, s_h)
+    assert 0.2 < s_h.mean() < 0.8 and np.isfinite(probs).all()
+    e = opt.local_energies(s)
+    if dtype == "f32":
+        e_ref = O.ising_local_energies(np.ones(N), 1.0, s_h, lambda c: O.log_probability(p, c))
+    else:
+        e_ref = O.ising2d_local_energies(np.ones((3, 4)), 1.0, 3, 4, s_h, lambda c: O.log_probability(p, c), flat=True)
+    np.testing.assert_allclose(e.cpu().numpy(), e_ref, rtol=max(tol, 1e-9))
+    mean, var, n = opt.moments(e)
+    g = opt.gradient(s, e, mean, n).cpu().numpy()
+    w = (e_ref - e_ref.mean()) / ns
+    g_ref = TG.gru_vmc_grad({k: v.astype(np.float64) for k, v in p.items()}, s_h, w)
+    assert g.shape == g_ref.shape
+    assert np.linalg.norm(g - g_ref) / np.linalg.norm(g_ref) < (1e-4 if dtype == "f32" else 1e-8)
+    before = wf.params.clone()
+    opt.apply(torch.as_tensor(g, device=wf.device), 1e-2)
+    assert float((wf.params - before).abs().max()) > 0 and wf.params.numel() == before.numel()
