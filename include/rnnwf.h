@@ -150,7 +150,8 @@ int rnnwf_energy_moments(const double* eloc, int64_t ns, int stride, double* sta
  * the dominant kernel of each call (the prefix-reuse chain kernel of rnnwf_tfim_eloc / rnnwf_j1j2_eloc) with
  * CUDA events on the caller's stream.  rnnwf_profile_end() waits for those events and returns the launch count,
  * the number of dominant-kernel launches and their summed device time.  Results of the compute entry points
- * are unaffected.  (The reference has only commented-out time.time() prints, 1DTFIM/TrainingRNN_1DTFIM.py:53-54.) */
+ * are unaffected; the counters are per calling host thread (like rnnwf_last_error), nothing is shared between threads.
+ * (The reference has only commented-out time.time() prints, 1DTFIM/TrainingRNN_1DTFIM.py:53-54.) */
 int rnnwf_profile_begin(void);
 int rnnwf_profile_end(int64_t* launches_out, int64_t* dominant_launches_out, double* dominant_ms_out);
 

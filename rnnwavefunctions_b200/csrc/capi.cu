@@ -10,9 +10,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-// measurement state (host only; one process per GPU, see include/rnnwf.h)
+// measurement state of rnnwf_profile_begin / end: host only and per calling thread, like the error string -- the library keeps no
+// state that two host threads (or two wave functions) share
 static constexpr int kProfPairs = 256;
-static struct {
+static thread_local struct {
     bool on = false;
     long launches = 0;
     int pairs = 0;
