@@ -283,3 +283,40 @@ def test_unequal_layer_widths_run_zero_padded(units, dtype):
     before = wf.params.clone()
     opt.apply(torch.as_tensor(g, device=wf.device), 1e-2)
     assert float((wf.params - before).abs().max()) > 0 and wf.params.numel() == before.numel()
+
+
+def test_wave_function_on_a_device_that_is_not_current():
+    """Every C-ABI wrapper runs with the device of its parameter tensor current (ops._on_device_of): a wave function built on cuda:1
+    works while cuda:0 is the current device and gives the numbers of the same model on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from rnnwavefunctions_b200.vmc import TFIM, VMC
+    from rnnwavefunctions_b200.wavefunction import RNNwavefunction1D
+    torch.cuda.set_device(0)
+    N, ns = 24, 300
+    res = []
+    for d in ("cuda:0", "cuda:1"):
+        wf = RNNwavefunction1D(N, units=[50, 50], seed=3, device=d)
+        opt = VMC(wf, TFIM(np.ones(N), 1.0), ns)
+        s = opt.draw()
+        e = opt.local_energies(s)
+        mean, var, n = opt.moments(e)
+        g = opt.gradient(s, e, mean, n)
+        opt.apply(g, 1e-2)
+        assert torch.cuda.current_device() == 0 and s.device == torch.device(d) and g.device == torch.device(d)
+        res.append((s.cpu(), e.cpu(), g.cpu(), wf.params.cpu()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+def test_wide_float32_stack_warns_once_and_runs_on_the_cuda_core_engine():
+    """float32 stacks wider than 50 units miss the tcgen05 kernels: the class says so (RuntimeWarning) and the FFMA engine gives the
+    oracle's numbers."""
+    from rnnwavefunctions_b200.wavefunction import RNNwavefunction1D
+    N, ns = 10, 64
+    with pytest.warns(RuntimeWarning, match="CUDA-core FFMA engine"):
+        wf = RNNwavefunction1D(N, units=[64], seed=2)
+    assert ops.tfim_chain_mode(wf.model) == 0
+    p = O.unflatten(wf.params.cpu().numpy(), O.gru_param_shapes([64]), np.float32)
+    s = wf.sample(ns).cpu().numpy()
+    np.testing.assert_allclose(wf.log_probability(s).cpu().numpy(), O.log_probability(p, s), rtol=1e-5)
