@@ -42,8 +42,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(Src src, int ct, int
     const int64_t b0 = src.nblk * ks / ksplit, b1 = src.nblk * (ks + 1) / ksplit;
     const int nsl = (M + kKS - 1) / kKS;
     const int64_t T = (b1 - b0) * nsl;
-    // fragments of this warp: 13 = 4 + 3 + 3 + 3 in both directions
-    const int wm = warp >> 2, wn = warp & 3;
+    // fragments of this warp: 13 = 4 + 3 + 3 + 3 in both directions.  Warp w issues on SM sub-partition w % 4; the column group is rotated
+    // by the row group so that every sub-partition gets 43 or 42 of the 169 fragments (unrotated: 52 / 39 / 39 / 39, and ncu showed the
+    // DMMA pipe 69 % active with math_pipe_throttle as the only stall)
+    const int wm = warp >> 2, wn = (warp + wm) & 3;
     const int mt0 = wm == 0 ? 0 : 1 + 3 * wm, nm = wm == 0 ? 4 : 3;
     const int nt0 = wn == 0 ? 0 : 1 + 3 * wn, nn = wn == 0 ? 4 : 3;
     double acc[4][4][2];
