@@ -141,7 +141,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
         const int s = BASE ? -1 : work / a.tiles64, tile = work % a.tiles64;  // slots in order of decreasing chain length
         // this lane's four rows (one per m-tile): global row -> (old tile, row in tile) of the base pass' layout
         size_t rbase[4];       // index of (old tile, site 0, row): + n * Mold for site n
-        size_t hbase[4];
         bool live[4];
         int otile[4], om[4];
 #pragma unroll
@@ -152,7 +151,6 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
             otile[mt] = (int)(R / Mold);
             om[mt] = (int)(R % Mold);
             rbase[mt] = (size_t)otile[mt] * N * Mold + om[mt];
-            hbase[mt] = 0;
         }
         // restart state: h after site s of the base pass (BASE: the zero state) -> buffer 0
         for (int i = tid; i < kRows * H; i += kThreads) {
@@ -269,11 +267,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_kernel(const __grid_constan
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
                 if (live[mt]) {
-                    if (BASE) a.lp[(size_t)otile[mt] * Mold + om[mt]] = acc[mt];
+                    if constexpr (BASE) a.lp[(size_t)otile[mt] * Mold + om[mt]] = acc[mt];
                     else a.delta[((size_t)otile[mt] * a.nslots + s) * Mold + om[mt]] = acc[mt];
                 }
         }
-        (void)hbase;
     }
 }
 

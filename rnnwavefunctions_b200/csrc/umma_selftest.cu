@@ -9,7 +9,6 @@
 
 namespace rnnwf {
 
-constexpr int kStRows = 128;
 
 // smem: B_hi | B_lo in the canonical K-major no-swizzle layout (LBO = 128 B between K chunks, SBO = KC * 128 B between
 // 8-row groups), then the mbarrier and the TMEM base address.
