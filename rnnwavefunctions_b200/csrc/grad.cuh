@@ -514,6 +514,9 @@ __global__ void __launch_bounds__(kWgfThreads) wgrad_fast_kernel(WgradArgs<float
 // half as large (110 instead of 198 KB at cfg2), so TWO CTAs share an SM: one splits / stores its operands or waits for its loads
 // while the tensor pipe works for the other, and twice as many loads are in flight (the one-CTA version was bound by the latency of
 // its one-block-deep register prefetch: ncu long_scoreboard 4.3 stalls per issue, tensor pipe 22 %, 1.87 TB/s of DRAM reads).
+#ifndef RNNWF_WGRAD_ASYNC
+#define RNNWF_WGRAD_ASYNC 1   // 1: operands go global -> shared by cp.async straight into the hi images (below); 0: register prefetch + split
+#endif
 namespace wgtc {
 constexpr int kThreads = 256, kMaxItems = 16;
 
@@ -613,6 +616,61 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_kernel(WgradArgs<float> a, 
         }
     }
     const int64_t hspan = (int64_t)a.L * a.H * M, gspan = (int64_t)a.cols * M;
+#if RNNWF_WGRAD_ASYNC
+    // Operand path without registers (round 2): kind::tf32 reads the upper 19 bits of an FP32 word and ignores the rest
+    // (scripts/tf32_raw_probe.py: the product of raw operands equals the product of the TRUNCATED operands to 6e-8), so the raw data
+    // are their own hi image: every thread copies its items global -> shared with cp.async (16 bytes = 4 samples of one row, which is
+    // one core-matrix row of the image), then computes lo = x - trunc(x) from shared memory into the lo image.  No load occupies a
+    // register while it is in flight; while this CTA waits for its copies the other CTA of the SM works.
+    auto copy_in = [&](int64_t vb) {
+        const int64_t blk = vb / nsub;
+        const int sub = (int)(vb - blk * nsub), m0 = sub * Ms;
+        const bool first_site = blk % a.N == 0, last = sub == nsub - 1;
+        const float* hb = a.hstore + blk * hspan + m0;
+        const float* gb = a.B + blk * gspan + m0;
+        const uint8_t* sb = a.sigT + blk * M + m0;
+#pragma unroll
+        for (int it = 0; it < kMaxItems; ++it) {
+            const int kind = dsc[it] & 3;
+            if (kind == kSkip) continue;
+            float* dst = img_hi + ((size_t)((dsc[it] >> 5) & 0xfff) << 2);
+            const int goff = dsc[it] >> 17;
+            const float* src = nullptr;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!(last && (dsc[it] & 8))) {
+                if (kind == kGate) src = gb + goff;
+                else if (kind == kStash) { if (!((dsc[it] & 4) && first_site)) src = hb + goff; }
+                else if (!first_site) {                                   // one-hot rows: computed, exact in TF32
+                    const uint32_t sg = *reinterpret_cast<const uint32_t*>(sb + goff);
+                    const int r = (dsc[it] >> 4) & 1;
+                    v.x = (int)(sg & 0xff) == r ? 1.f : 0.f;
+                    v.y = (int)((sg >> 8) & 0xff) == r ? 1.f : 0.f;
+                    v.z = (int)((sg >> 16) & 0xff) == r ? 1.f : 0.f;
+                    v.w = (int)(sg >> 24) == r ? 1.f : 0.f;
+                }
+            }
+            if (src != nullptr) cp_async16(dst, src);
+            else *reinterpret_cast<float4*>(dst) = v;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto make_lo = [&]() {
+        asm volatile("cp.async.wait_all;" ::: "memory");                  // this thread's own copies: it reads only what it copied
+#pragma unroll
+        for (int it = 0; it < kMaxItems; ++it) {
+            if ((dsc[it] & 3) != kSkip) {
+                const size_t o = (size_t)((dsc[it] >> 5) & 0xfff) << 2;
+                const float4 x = *reinterpret_cast<const float4*>(img_hi + o);
+                float4 lo;
+                lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4*>(img_lo + o) = lo;
+            }
+        }
+    };
+#else
     float4 pre[kMaxItems];
     auto prefetch = [&](int64_t vb) {
         const int64_t blk = vb / nsub;
@@ -640,11 +698,18 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_kernel(WgradArgs<float> a, 
             pre[it] = v;
         }
     };
+#endif
     uint32_t commits = 0;
     int pending = 0;
+#if !RNNWF_WGRAD_ASYNC
     if (b0 < b1) prefetch(b0);
+#endif
     for (int64_t blk = b0; blk < b1; ++blk) {
         if (commits > 0) umma::mbar_wait(bar, (commits - 1) & 1);        // the previous block's MMAs have read the images
+#if RNNWF_WGRAD_ASYNC
+        copy_in(blk);
+        make_lo();
+#else
 #pragma unroll
         for (int it = 0; it < kMaxItems; ++it) {
             if ((dsc[it] & 3) != kSkip) {
@@ -658,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_kernel(WgradArgs<float> a, 
                 *reinterpret_cast<float4*>(img_lo + o) = lo;
             }
         }
+#endif
         umma::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -673,7 +739,9 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_kernel(WgradArgs<float> a, 
             umma::commit(bar);
         }
         ++commits;
+#if !RNNWF_WGRAD_ASYNC
         if (blk + 1 < b1) prefetch(blk + 1);                             // in flight while the tensor pipe works
+#endif
         if (++pending == kWgFlush * nsub || blk + 1 == b1) {      // the same number of samples per FP32 accumulator as with whole blocks
             umma::mbar_wait(bar, (commits - 1) & 1);
             umma::fence_after_sync();

@@ -31,7 +31,10 @@ umma_selftest_kernel(int N, int K, const float* __restrict__ A, const float* __r
     for (int i = tid; i < N * Kp; i += blockDim.x) {
         const int n = i / Kp, k = i % Kp;
         float hi = 0.f, lo = 0.f;
-        if (k < K) umma::split_tf32(B[n * K + k], hi, lo);
+        if (k < K) {
+            if (passes == 4) hi = B[n * K + k];          // probe: raw FP32 bits as kind::tf32 operands (what does the tensor core do with the low 13?)
+            else umma::split_tf32(B[n * K + k], hi, lo);
+        }
         const int off = (n / 8) * (KC * 32) + (k / 4) * 32 + (n % 8) * 4 + (k % 4);   // in floats
         Bhi[off] = hi;
         Blo[off] = lo;
@@ -51,7 +54,10 @@ umma_selftest_kernel(int N, int K, const float* __restrict__ A, const float* __r
             for (int q = 0; q < 8; ++q) {
                 const int k = k0 + q;
                 hi[q] = 0.f; lo[q] = 0.f;
-                if (k < K) umma::split_tf32(A[tid * K + k], hi[q], lo[q]);
+                if (k < K) {
+                    if (passes == 4) hi[q] = A[tid * K + k];
+                    else umma::split_tf32(A[tid * K + k], hi[q], lo[q]);
+                }
             }
             umma::tmem_st8(lane_addr + colAhi + k0, hi);
             umma::tmem_st8(lane_addr + colAlo + k0, lo);
@@ -65,7 +71,7 @@ umma_selftest_kernel(int N, int K, const float* __restrict__ A, const float* __r
         const uint32_t idesc = umma::instr_desc(umma::kFmtTF32, 128, N);
         const uint32_t bhi = umma::smem_u32(Bhi), blo = umma::smem_u32(Blo);
         uint32_t acc = 0;
-        for (int pass = 0; pass < passes; ++pass) {
+        for (int pass = 0; pass < (passes == 4 ? 1 : passes); ++pass) {
             const uint32_t acol = pass == 1 ? colAlo : colAhi;       // hi*hi, lo*hi, hi*lo
             const uint32_t bsm = pass == 2 ? blo : bhi;
             for (int ks = 0; ks < Kp / 8; ++ks) {
@@ -361,8 +367,8 @@ int umma_selftest_f16_impl(int N, int K, const float* A, const float* B, float* 
 }
 
 int umma_selftest_impl(int N, int K, const float* A, const float* B, float* D, int passes, cudaStream_t s) {
-    RNNWF_CHECK(N >= 16 && N <= 256 && N % 16 == 0 && K >= 1 && K <= 64 && (passes == 1 || passes == 3), -1,
-                "umma selftest: N in [16,256] multiple of 16, K <= 64, passes 1 or 3");
+    RNNWF_CHECK(N >= 16 && N <= 256 && N % 16 == 0 && K >= 1 && K <= 64 && (passes == 1 || passes == 3 || passes == 4), -1,
+                "umma selftest: N in [16,256] multiple of 16, K <= 64, passes 1 or 3 (4: raw FP32 operands, one pass)");
     const int Kp = (K + 7) & ~7;
     const int smem = 2 * N * Kp * 4 + 64;
     RNNWF_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
