@@ -1,4 +1,5 @@
 #!/bin/bash
+# Development aid: per-kernel times (ncu launch list) of gradient calls at 10^4 samples for build/variants/lib_<name>.so.
 cd "$(dirname "$0")/.."
 for v in "$@"; do
   echo "== $v (ncu launch list, gradient calls at 10^4 samples)"
