@@ -525,12 +525,16 @@ struct Geo {
     int Ms, nsub;                               // samples per slice (multiple of 4), slices per block
     size_t img_floats, smem;
 };
-inline Geo make_geo(int R, int cols, int M) {
+inline Geo make_geo(int R, int cols, int M, int nsub = 0) {
     Geo q;
     q.Rp8 = (R + 7) / 8 * 8;
     q.Cp8 = (cols + 7) / 8 * 8;
     q.Np = (cols + 15) / 16 * 16;
-    q.nsub = M > 40 ? 2 : 1;
+    if (nsub == 0) {   // whole blocks while two CTAs still share an SM (narrow outputs: the head weights), else two slices
+        const Geo whole = make_geo(R, cols, M, 1);
+        nsub = (whole.smem <= (size_t)(kSmemLimit / 2 - 1024) && whole.nit <= kMaxItems && whole.img_floats / 4 < 4096) ? 1 : (M > 40 ? 2 : 1);
+    }
+    q.nsub = nsub;
     q.Ms = ((M + q.nsub - 1) / q.nsub + 3) / 4 * 4;
     q.Kp = (q.Ms + 7) / 8 * 8;
     q.M4p = (q.Ms / 4 + 3) / 4 * 4;
